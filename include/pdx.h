@@ -1,0 +1,183 @@
+/*
+ * pdx.h - C ABI of libpdx.so: B200 (sm_100a) kernels for PDEnsorflow's monodomain
+ * time-stepping hot path.
+ *
+ * The reference (cesare-corrado/PDEnsorflow) has no FFI layer: its hot path is reached
+ * through three Python contracts (operator functions, the IonicModel protocol, the
+ * HeatSolver/MonodomainSolver classes) that bottom out in TensorFlow ops.  The entry
+ * points below are what a Python shim for those contracts binds with ctypes; each one
+ * cites the reference interface it replaces (paths relative to
+ * /root/reference/PDEnsorflow/).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, POD structs.  No torch / C++ types.
+ *  - all field buffers are DEVICE pointers owned by the caller (fp32, contiguous,
+ *    C order, last axis contiguous); the library never frees or retains them beyond
+ *    the call (tensor-map caches are keyed by pointer value only).
+ *  - every compute call takes a cudaStream_t (passed as void*) and is asynchronous and
+ *    stream ordered, so it can be captured into a CUDA graph.
+ *  - return value: 0 = ok, non-zero = error; pdx_last_error() gives the message
+ *    (thread local).  No CPU fallback exists: without a CUDA device every compute
+ *    call fails.
+ *  - axis naming: arrays are [nx][ny][nz], nz contiguous.  The reference's
+ *    [width, height, depth] maps to nx=width, ny=height, nz=depth (DX,DY,DZ likewise);
+ *    2-D fields [W,H] use nx=1, ny=W, nz=H (dy=DX, dz=DY).
+ */
+#ifndef PDX_H
+#define PDX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDX_VERSION 100
+
+/* ionic models: gpuSolve/ionic/{fenton4v,mms2v,ms2v}.py */
+enum { PDX_MODEL_NONE = 0, PDX_MODEL_FENTON4V = 1, PDX_MODEL_MMS2V = 2, PDX_MODEL_MS2V = 3 };
+/* diffusion operators: gpuSolve/diffop3D/__init__.py:25-28, diffop2D/__init__.py:20-21 */
+enum { PDX_LAP_HOMOG = 0, PDX_LAP_CONV = 1, PDX_LAP_HETEROG = 2 };
+/* arithmetic: EXACT = op-for-op fp32 in the reference's evaluation order, IEEE division,
+ * no FMA contraction, correctly rounded tanh.  FAST = same formulas with reciprocal
+ * multiplies, FMA contraction and ex2/rcp-based tanh (|err| ~1e-7); meets the
+ * north-star tolerance (rel-L2 <= 1e-5) and is what bench.py times. */
+enum { PDX_MATH_EXACT = 0, PDX_MATH_FAST = 1 };
+/* kernel selection for the fused FD step */
+enum { PDX_KERNEL_AUTO = 0, PDX_KERNEL_GENERIC = 1, PDX_KERNEL_TMA = 2 };
+
+#define PDX_MAX_PARAMS 24
+#define PDX_MAX_STATES 4
+
+/* Parameter vector layouts (fp32, the reference's defaults are returned by
+ * pdx_model_default_params):
+ *  FENTON4V (fenton4v.py:56-78): tau_vp tau_vn tau_wp tau_wn1 tau_wn2 tau_d tau_si tau_so
+ *      tau_a u_c u_w u_0 u_m u_csi u_so r_sp r_sn k_ a_so b_so c_so vmin DV     (23)
+ *  MMS2V (mms2v.py:47-55):  tau_in tau_out tau_open tau_close u_gate u_crit vmin DV (8)
+ *  MS2V  (ms2v.py:46-53):   tau_in tau_out tau_open tau_close u_gate  -     vmin DV (8)
+ *  (DV is the models' _DV attribute = vmax - vmin formed in fp32 at construction.)
+ * State arrays: FENTON4V V,W,S (init 1,1,0); MMS2V/MS2V H (init 1). */
+int pdx_model_num_params(int model);
+int pdx_model_num_states(int model);
+int pdx_model_default_params(int model, float* out /* PDX_MAX_PARAMS */);
+
+/* Descriptor of one fused explicit FD step:
+ *   U1 = (U0 + dt*dU(U)) + coef*lap(U0)       U0 = enforce_boundary(U)
+ * replaces the body of the examples' solve(): Tests/FD/Fenton/fenton.py:90-99,
+ * Tests/FD/Fenton_sphere/fenton.py:109-115, Tests/FD/HeatEquation/heat.py:86-94
+ * = enforce_boundary (fenton.py:46-53) + IonicModel.differentiate
+ * (fenton4v.py:168-185 / mms2v.py:95-105 / ms2v.py:90-100) + laplace_* + Euler update.
+ *
+ * Slab decomposition: the arrays hold nx planes of which [x_begin, x_end) are advanced;
+ * plane indices used by the stencil are clamped to [x_clamp_lo, x_clamp_hi].  A
+ * stand-alone grid uses x_begin=0, x_end=nx, clamp [1, nx-2]; an interior slab with one
+ * ghost plane per side uses x_begin=1, x_end=nx-1, clamp [0, nx-1] (ghost planes are
+ * filled by the caller's halo exchange). */
+typedef struct pdx_fd_desc {
+    int32_t ndim;            /* 2 or 3 */
+    int32_t nx, ny, nz;      /* array extents (nx = 1 for 2-D) */
+    float   dx, dy, dz;      /* spacings of the nx/ny/nz axes (dx ignored for 2-D) */
+    float   dt;              /* f32(dt): multiplies dU and advances the gates */
+    float   coef;            /* f32(diff*dt) for HOMOG/CONV, f32(dt) for HETEROG */
+    int32_t lap_kind;        /* PDX_LAP_* */
+    int32_t model;           /* PDX_MODEL_* (NONE = heat equation) */
+    int32_t math_mode;       /* PDX_MATH_* */
+    int32_t kernel;          /* PDX_KERNEL_* */
+    int32_t x_begin, x_end;  /* planes advanced by a step */
+    int32_t x_clamp_lo, x_clamp_hi;
+    int32_t dirichlet;       /* 0: symmetric clamp (Neumann); 1: constant boundary
+                                (Tests/FD/LaplaceSolver/laplaceSolver.py:44-52) */
+    float   dirichlet_value;
+    int32_t x_chunk;         /* planes marched per CTA by the TMA kernel; 0 = auto */
+    float   params[PDX_MAX_PARAMS];
+} pdx_fd_desc;
+
+typedef struct pdx_fd_plan pdx_fd_plan;
+
+void pdx_fd_desc_init(pdx_fd_desc* d);                      /* zero + defaults */
+int  pdx_fd_plan_create(const pdx_fd_desc* d, pdx_fd_plan** out);
+void pdx_fd_plan_destroy(pdx_fd_plan* p);
+/* which kernel a plan resolved to (PDX_KERNEL_GENERIC / PDX_KERNEL_TMA) */
+int  pdx_fd_plan_kernel(const pdx_fd_plan* p);
+/* number of kernel launches issued through this plan so far */
+int64_t pdx_fd_plan_launches(const pdx_fd_plan* p);
+
+/* nsteps fused steps, ping-ponging between U_a and U_b: step k reads (k even ? U_a : U_b)
+ * and writes the other; the result is in U_b when nsteps is odd, in U_a when even.
+ * states[]: the model's state arrays, updated in place.  DIFF: diffusivity field for
+ * PDX_LAP_HETEROG (else NULL).  All arrays have the descriptor's [nx][ny][nz] shape. */
+int pdx_fd_step(pdx_fd_plan* p, float* U_a, float* U_b, float* const* states,
+                const float* DIFF, int nsteps, void* stream);
+/* one step restricted to planes [xb, xe) (boundary-first / interior split used to
+ * overlap the halo exchange); same clamps as the plan. */
+int pdx_fd_step_range(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states,
+                      const float* DIFF, int xb, int xe, void* stream);
+
+/* Stand-alone operators (pure functions, new output array) - contract 1:
+ * gpuSolve/diffop3D/laplace_homogeneous_isotropic_diffusion.py:3-52,
+ * laplace_convolution_homogeneous_isotropic_diffusion.py:4-47,
+ * laplace_heterogeneous_isotropic_diffusion.py:3-35, and the diffop2D analogues
+ * (diffop2D/laplace_homogeneous_isotropic_diffusion.py:3-36,
+ *  laplace_heterogeneous_isotropic_diffusion.py:3-32).  Symmetric pad of X0 (and DIFF). */
+int pdx_fd_laplace(int ndim, int nx, int ny, int nz, float dx, float dy, float dz,
+                   int lap_kind, int math_mode, const float* X0, const float* DIFF,
+                   float* out, void* stream);
+/* enforce_boundary: Tests/FD/Fenton/fenton.py:46-53 (dirichlet=0) /
+ * LaplaceSolver/laplaceSolver.py:44-52 (dirichlet=1) */
+int pdx_fd_enforce_boundary(int ndim, int nx, int ny, int nz, int dirichlet, float value,
+                            const float* X, float* out, void* stream);
+
+/* IonicModel.differentiate(U) - contract 2 (fenton4v.py:168-185, mms2v.py:95-105,
+ * ms2v.py:90-100): writes dU, advances states in place by dt.  param_arrays (may be
+ * NULL): per-parameter device pointers to per-node values installed through
+ * set_parameter (ionicmodel.py:56-62); NULL entries use params[i].
+ * If U1_out != NULL the kernel also writes rhs0 = U + dt*(dU + I0) (I0 may be NULL):
+ * the RHS0 of MonodomainSolver.solve_step (monodomainSolver.py:100-103). */
+int pdx_ionic_step(int model, int math_mode, const float* params,
+                   const float* const* param_arrays, int64_t n, const float* U,
+                   float* const* states, float* dU_out, float dt,
+                   const float* I0, float* rhs0_out, void* stream);
+
+/* Stimulus application of the FD examples (Tests/FD/Fenton/fenton.py:154-156):
+ * U = mask ? max(U, intensity*mask) : U, mask as produced by Stimulus.set_stimregion
+ * (force_terms/stimulus.py:73-80). */
+int pdx_stim_apply(float* U, const float* mask, float intensity, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ FEM path */
+/* y = A x, CSR fp32 / int32 (replaces tf.raw_ops.SparseMatrixMatMul with a [N,1]
+ * operand: linearsolvers/conjgrad.py:99-101, monodomainSolver.py:104, heatSolver.py:132) */
+int pdx_csr_spmv(int32_t n, const int32_t* rowptr, const int32_t* col, const float* val,
+                 const float* x, float* y, void* stream);
+
+/* Jacobi-preconditioned CG - contract 3 (linearsolvers/conjgrad.py:172-203,257-312;
+ * jacobi_precond.py:19-41).  One persistent cooperative kernel runs the whole solve:
+ * r=b-Ax; z=Minv*r; p=z; loop {q=Ap; alpha=rz/(p.q); x+=alpha p; r-=alpha q; res=r.r;
+ * z=Minv*r; rz'=r.z; beta=rz'/rz; p=z+beta p; every check_every its: stop if !finite(res)
+ * or res < toll^2}.  x holds X0 on entry and the solution on exit.
+ * info (device, 2 floats + 2 ints packed as 4 x 4 bytes): [0] int niters, [1] float res,
+ * [2] int flags (bit0 = maxiter reached, bit1 = non-finite), [3] reserved. */
+typedef struct pdx_pcg pdx_pcg;
+int  pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const float* val,
+                    const float* minv /* may be NULL: no preconditioner */, pdx_pcg** out);
+void pdx_pcg_destroy(pdx_pcg* s);
+int  pdx_pcg_solve(pdx_pcg* s, const float* b, float* x, int maxiter, double toll,
+                   int check_every, int32_t* info /* device, 4 words */, void* stream);
+
+/* Explicit mass-lumped FEM step named by the north star (no reference implementation;
+ * SURVEY.md section 8a row E): U1 = U + dt*(dU + I0) - dt * mlinv * (K U), fused with the
+ * ionic update (row-per-warp CSR). */
+int pdx_fem_explicit_step(int model, int math_mode, const float* params, int32_t n,
+                          const int32_t* rowptr, const int32_t* col, const float* kval,
+                          const float* mlinv, const float* U_in, float* U_out,
+                          float* const* states, const float* I0, float dt, void* stream);
+
+/* ------------------------------------------------------------------ misc */
+int         pdx_version(void);
+const char* pdx_last_error(void);
+/* total kernel launches issued by this library in this process */
+int64_t     pdx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDX_H */

@@ -1,0 +1,79 @@
+"""Build libpdx.so (sm_100a) in-tree with nvcc.  No GPU needed (cross-compiles).
+
+    python pdensorflow_b200/csrc/build.py [--force] [--verbose]
+
+Objects go to pdensorflow_b200/csrc/build/, the library to pdensorflow_b200/libpdx.so.
+A source is recompiled when it (or any header next to it) is newer than its object.
+"""
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+ROOT = os.path.dirname(PKG)
+BUILD = os.path.join(HERE, 'build')
+LIB = os.path.join(PKG, 'libpdx.so')
+SOURCES = ['pdx_api.cu', 'pdx_fd_generic.cu', 'pdx_fd_tma.cu', 'pdx_fem.cu']
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
+         '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def _headers():
+    hs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.h', '.cuh'))]
+    hs.append(os.path.join(ROOT, 'include', 'pdx.h'))
+    return hs
+
+
+def _stale(src, obj):
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(f) > t for f in [src] + _headers())
+
+
+def build(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(HERE, s)
+        obj = os.path.join(BUILD, s.replace('.cu', '.o'))
+        if force or _stale(src, obj):
+            cmd = [nvcc] + ARCH + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            jobs.append((s, cmd))
+
+    def run(job):
+        name, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return name, r
+
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for name, r in ex.map(run, jobs):
+                if verbose or r.returncode != 0:
+                    sys.stderr.write('--- %s\n%s%s\n' % (name, r.stdout, r.stderr))
+                if r.returncode != 0:
+                    raise RuntimeError('nvcc failed on %s' % name)
+    objs = [os.path.join(BUILD, s.replace('.cu', '.o')) for s in SOURCES]
+    if jobs or not os.path.exists(LIB):
+        cmd = [nvcc] + ARCH + ['-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('link failed')
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

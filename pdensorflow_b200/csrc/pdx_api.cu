@@ -1,0 +1,352 @@
+// pdx_api.cu - the C ABI of libpdx.so (see include/pdx.h): plans, tensor maps, dispatch.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <unordered_map>
+#include "pdx_internal.h"
+
+namespace pdx {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return 1;
+}
+
+static const float kFkDefaults[FK_NPARAM] = {3.33f, 19.2f, 160.0f, 75.0f, 75.0f, 0.065f, 31.8364f, 31.8364f, 0.009f,
+                                             0.23f, 0.146f, 0.0f, 1.0f, 0.8f, 0.3f, 0.02f, 1.2f, 3.0f,
+                                             0.115f, 0.84f, 0.02f, -80.0f, 100.0f};
+static const float kMmsDefaults[MS_NPARAM] = {0.1f, 9.0f, 100.0f, 120.0f, 0.13f, 0.13f, -80.0f, 100.0f};
+static const float kMsDefaults[MS_NPARAM]  = {0.3f, 6.0f, 120.0f, 150.0f, 0.13f, 0.0f, -80.0f, 100.0f};
+
+void fill_model_params(int model, const float* params, float dt, ModelParams* out) {
+    std::memset(out, 0, sizeof(*out));
+    out->dt = dt;
+    const int np = pdx_model_num_params(model);
+    for (int i = 0; i < np; ++i) {
+        out->p[i] = params[i];
+        out->r[i] = params[i] != 0.0f ? (float)(1.0 / (double)params[i]) : 0.0f;
+    }
+    const double log2e = 1.4426950408889634;
+    if (model == PDX_MODEL_FENTON4V) {
+        out->DV  = params[FK_DV];
+        out->rDV = out->r[FK_DV];
+        out->d0  = (float)(-2.0 * log2e / (double)params[FK_c_so]);
+        out->d1  = (float)(-2.0 * log2e * (double)params[FK_k]);
+        out->d2  = params[FK_a_so] - params[FK_tau_a];     // fp32, as the reference forms it
+        out->d3  = params[FK_r_sp] - params[FK_r_sn];
+    } else if (model == PDX_MODEL_MMS2V || model == PDX_MODEL_MS2V) {
+        out->DV  = params[MS_DV];
+        out->rDV = out->r[MS_DV];
+    }
+}
+
+static CUresult encode_tiled(CUtensorMap* map, void* base, const cuuint64_t* gdim, const cuuint64_t* gstride,
+                             const cuuint32_t* box) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p ||
+            qres != cudaDriverEntryPointSuccess)
+            return CUDA_ERROR_NOT_FOUND;
+        fn = (EncodeFn)p;
+    }
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+int make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int nz, int box_x, int box_y,
+                       int box_z) {
+    const cuuint64_t gdim[3]    = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx};
+    const cuuint64_t gstride[2] = {(cuuint64_t)nz * 4, (cuuint64_t)nz * ny * 4};
+    const cuuint32_t box[3]     = {(cuuint32_t)box_z, (cuuint32_t)box_y, (cuuint32_t)box_x};
+    const CUresult r = encode_tiled(map, const_cast<float*>(base), gdim, gstride, box);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult " + std::to_string((int)r) + ")");
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace pdx
+
+using namespace pdx;
+
+struct pdx_fd_plan {
+    pdx_fd_desc d;
+    int kernel;
+    FdArgs base;
+    int box_y, box_z;
+    std::unordered_map<const void*, CUtensorMap> maps;
+    int64_t launches;
+};
+
+static int get_map(pdx_fd_plan* p, const float* ptr, const CUtensorMap** out) {
+    auto it = p->maps.find(ptr);
+    if (it == p->maps.end()) {
+        CUtensorMap m;
+        if (make_tensor_map_3d(&m, ptr, p->d.nx, p->d.ny, p->d.nz, 1, p->box_y, p->box_z)) return 1;
+        if (p->maps.size() > 64) p->maps.clear();
+        it = p->maps.emplace(ptr, m).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+extern "C" {
+
+int pdx_version(void) { return PDX_VERSION; }
+const char* pdx_last_error(void) { return g_err.c_str(); }
+int64_t pdx_launch_count(void) { return g_launches.load(); }
+
+int pdx_model_num_params(int model) {
+    switch (model) {
+        case PDX_MODEL_NONE: return 0;
+        case PDX_MODEL_FENTON4V: return FK_NPARAM;
+        case PDX_MODEL_MMS2V:
+        case PDX_MODEL_MS2V: return MS_NPARAM;
+    }
+    return -1;
+}
+int pdx_model_num_states(int model) {
+    switch (model) {
+        case PDX_MODEL_NONE: return 0;
+        case PDX_MODEL_FENTON4V: return 3;
+        case PDX_MODEL_MMS2V:
+        case PDX_MODEL_MS2V: return 1;
+    }
+    return -1;
+}
+int pdx_model_default_params(int model, float* out) {
+    const int np = pdx_model_num_params(model);
+    if (np < 0 || !out) { set_error("pdx_model_default_params: bad arguments"); return 1; }
+    for (int i = 0; i < PDX_MAX_PARAMS; ++i) out[i] = 0.0f;
+    const float* src = model == PDX_MODEL_FENTON4V ? kFkDefaults : model == PDX_MODEL_MMS2V ? kMmsDefaults : kMsDefaults;
+    for (int i = 0; i < np; ++i) out[i] = src[i];
+    return 0;
+}
+
+void pdx_fd_desc_init(pdx_fd_desc* d) {
+    std::memset(d, 0, sizeof(*d));
+    d->ndim = 3;
+    d->dx = d->dy = d->dz = 1.0f;
+    d->math_mode = PDX_MATH_FAST;
+    d->kernel = PDX_KERNEL_AUTO;
+    d->x_begin = -1;   // resolved in plan_create
+}
+
+static int fill_args(const pdx_fd_desc& d, FdArgs* a) {
+    std::memset(a, 0, sizeof(*a));
+    a->nx = d.nx; a->ny = d.ny; a->nz = d.nz;
+    a->has_x = d.ndim == 3;
+    a->xb = d.x_begin; a->xe = d.x_end;
+    if (a->has_x) {
+        a->xclo = d.x_clamp_lo; a->xchi = d.x_clamp_hi;
+        a->dxlo = a->xclo - 1 > 0 ? a->xclo - 1 : 0;
+        a->dxhi = a->xchi + 1 < d.nx - 1 ? a->xchi + 1 : d.nx - 1;
+    }
+    a->yclo = 1; a->ychi = d.ny - 2;
+    a->zclo = 1; a->zchi = d.nz - 2;
+    a->dirichlet = d.dirichlet; a->dirichlet_value = d.dirichlet_value;
+    a->dt = d.dt; a->coef = d.coef;
+    a->hxsq = d.dx * d.dx; a->hysq = d.dy * d.dy; a->hzsq = d.dz * d.dz;
+    a->rhxsq = (float)(1.0 / (double)a->hxsq);
+    a->rhysq = (float)(1.0 / (double)a->hysq);
+    a->rhzsq = (float)(1.0 / (double)a->hzsq);
+    // conv taps, laplace_convolution_homogeneous_isotropic_diffusion.py:26-40: the kernel as
+    // written puts 1/dzsq on the axis-0 neighbours and 1/dxsq on the axis-2 neighbours
+    const float ix = 1.0f / a->hxsq, iy = 1.0f / a->hysq, iz = 1.0f / a->hzsq;
+    a->kx = iz; a->ky = iy; a->kz = ix;
+    a->kc = -2.0f * ((ix + iy) + iz);
+    fill_model_params(d.model, d.params, d.dt, &a->mp);
+    return 0;
+}
+
+int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
+    if (!din || !out) { set_error("pdx_fd_plan_create: null argument"); return 1; }
+    pdx_fd_desc d = *din;
+    if (d.ndim != 2 && d.ndim != 3) { set_error("pdx_fd_plan_create: ndim must be 2 or 3"); return 1; }
+    if (d.ndim == 2 && d.nx != 1) { set_error("pdx_fd_plan_create: 2-D fields use nx = 1"); return 1; }
+    if (d.ny < 3 || d.nz < 3 || (d.ndim == 3 && d.nx < 3)) {
+        set_error("pdx_fd_plan_create: every active axis needs at least 3 cells");
+        return 1;
+    }
+    if (pdx_model_num_states(d.model) < 0) { set_error("pdx_fd_plan_create: unknown model"); return 1; }
+    if (d.lap_kind < PDX_LAP_HOMOG || d.lap_kind > PDX_LAP_HETEROG) { set_error("pdx_fd_plan_create: unknown lap_kind"); return 1; }
+    if (d.lap_kind == PDX_LAP_CONV && d.ndim == 2) { set_error("pdx_fd_plan_create: the conv operator is 3-D only"); return 1; }
+    if (d.math_mode != PDX_MATH_EXACT && d.math_mode != PDX_MATH_FAST) { set_error("pdx_fd_plan_create: unknown math_mode"); return 1; }
+    if (d.ndim == 2) {
+        d.x_begin = 0; d.x_end = 1; d.x_clamp_lo = 0; d.x_clamp_hi = 0;
+    } else if (d.x_begin < 0) {   // stand-alone grid defaults
+        d.x_begin = 0; d.x_end = d.nx; d.x_clamp_lo = 1; d.x_clamp_hi = d.nx - 2;
+    }
+    if (d.x_begin < 0 || d.x_end > d.nx || d.x_begin > d.x_end || d.x_clamp_lo < 0 || d.x_clamp_hi > d.nx - 1 ||
+        d.x_clamp_lo > d.x_clamp_hi) {
+        set_error("pdx_fd_plan_create: inconsistent x range / clamp");
+        return 1;
+    }
+    int kernel = d.kernel;
+    const bool tma_ok = fd_tma_supported(d);
+    if (kernel == PDX_KERNEL_AUTO) kernel = tma_ok ? PDX_KERNEL_TMA : PDX_KERNEL_GENERIC;
+    if (kernel == PDX_KERNEL_TMA && !tma_ok) {
+        set_error("pdx_fd_plan_create: TMA kernel needs nz % 4 == 0, no Dirichlet, no EXACT conv");
+        return 1;
+    }
+    pdx_fd_plan* p = new (std::nothrow) pdx_fd_plan();
+    if (!p) { set_error("out of memory"); return 1; }
+    p->d = d;
+    p->kernel = kernel;
+    p->launches = 0;
+    fill_args(d, &p->base);
+    int ty, tz;
+    fd_tma_tile_geometry(d, &ty, &tz, &p->box_y, &p->box_z);
+    p->base.nty = (d.ny + ty - 1) / ty;
+    p->base.ntz = (d.nz + tz - 1) / tz;
+    p->base.x_chunk = d.x_chunk > 0 ? d.x_chunk : fd_tma_auto_chunk(d);
+    if (kernel == PDX_KERNEL_TMA) {
+        // set the kernel's shared-memory attribute now (an empty range launches nothing), so
+        // that the first real step can already be inside a CUDA-graph capture
+        FdArgs a = p->base;
+        a.xb = a.xe = 0;
+        CUtensorMap dummy;
+        std::memset(&dummy, 0, sizeof(dummy));
+        pdx_fd_desc dd = d;
+        if (dd.lap_kind == PDX_LAP_CONV) dd.lap_kind = PDX_LAP_HOMOG;
+        if (launch_fd_tma(dd, a, dummy, dummy, nullptr)) { delete p; return 1; }
+    }
+    *out = p;
+    return 0;
+}
+
+void pdx_fd_plan_destroy(pdx_fd_plan* p) { delete p; }
+int pdx_fd_plan_kernel(const pdx_fd_plan* p) { return p ? p->kernel : -1; }
+int64_t pdx_fd_plan_launches(const pdx_fd_plan* p) { return p ? p->launches : -1; }
+
+static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const* states, const float* DIFF, int xb,
+                     int xe, cudaStream_t s) {
+    const pdx_fd_desc& d = p->d;
+    if (!Uin || !Uout || Uin == Uout) { set_error("pdx_fd_step: U_in/U_out must be distinct non-null buffers"); return 1; }
+    const int ns = pdx_model_num_states(d.model);
+    if (ns > 0 && !states) { set_error("pdx_fd_step: states required"); return 1; }
+    if (d.lap_kind == PDX_LAP_HETEROG && !DIFF) { set_error("pdx_fd_step: DIFF required for the heterogeneous operator"); return 1; }
+    FdArgs a = p->base;
+    a.Uin = Uin; a.Uout = Uout; a.DIFF = DIFF;
+    for (int i = 0; i < ns; ++i) {
+        if (!states[i]) { set_error("pdx_fd_step: null state array"); return 1; }
+        a.st[i] = states[i];
+    }
+    a.xb = xb; a.xe = xe;
+    if (xe <= xb) return 0;
+    int kernel = p->kernel;
+    if (kernel == PDX_KERNEL_TMA) {
+        bool aligned = ((uintptr_t)Uin % 16 == 0) && ((uintptr_t)Uout % 16 == 0) &&
+                       (!DIFF || (uintptr_t)DIFF % 16 == 0);
+        for (int i = 0; i < ns; ++i) aligned = aligned && ((uintptr_t)states[i] % 16 == 0);
+        if (!aligned) {
+            if (d.kernel == PDX_KERNEL_TMA) { set_error("pdx_fd_step: TMA kernel needs 16-byte aligned arrays"); return 1; }
+            kernel = PDX_KERNEL_GENERIC;
+        }
+    }
+    int rc;
+    if (kernel == PDX_KERNEL_TMA) {
+        const CUtensorMap* mU = nullptr;
+        const CUtensorMap* mD = nullptr;
+        if (get_map(p, Uin, &mU)) return 1;
+        if (d.lap_kind == PDX_LAP_HETEROG) { if (get_map(p, DIFF, &mD)) return 1; } else mD = mU;
+        pdx_fd_desc dd = d;
+        if (dd.lap_kind == PDX_LAP_CONV) dd.lap_kind = PDX_LAP_HOMOG;   // FAST conv alias
+        rc = launch_fd_tma(dd, a, *mU, *mD, s);
+    } else {
+        rc = launch_fd_generic(d, a, s);
+    }
+    if (!rc) p->launches += 1;
+    return rc;
+}
+
+int pdx_fd_step(pdx_fd_plan* p, float* U_a, float* U_b, float* const* states, const float* DIFF, int nsteps,
+                void* stream) {
+    if (!p) { set_error("pdx_fd_step: null plan"); return 1; }
+    for (int k = 0; k < nsteps; ++k) {
+        const float* in = (k & 1) ? U_b : U_a;
+        float* outp = (k & 1) ? U_a : U_b;
+        if (step_once(p, in, outp, states, DIFF, p->d.x_begin, p->d.x_end, (cudaStream_t)stream)) return 1;
+    }
+    return 0;
+}
+
+int pdx_fd_step_range(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states, const float* DIFF,
+                      int xb, int xe, void* stream) {
+    if (!p) { set_error("pdx_fd_step_range: null plan"); return 1; }
+    if (xb < p->d.x_begin || xe > p->d.x_end) { set_error("pdx_fd_step_range: range outside the plan's planes"); return 1; }
+    return step_once(p, U_in, U_out, states, DIFF, xb, xe, (cudaStream_t)stream);
+}
+
+int pdx_fd_laplace(int ndim, int nx, int ny, int nz, float dx, float dy, float dz, int lap_kind, int math_mode,
+                   const float* X0, const float* DIFF, float* out, void* stream) {
+    if (!X0 || !out) { set_error("pdx_fd_laplace: null array"); return 1; }
+    if ((ndim != 2 && ndim != 3) || (ndim == 2 && nx != 1) || nx < 1 || ny < 1 || nz < 1) {
+        set_error("pdx_fd_laplace: bad shape");
+        return 1;
+    }
+    if (lap_kind == PDX_LAP_HETEROG && !DIFF) { set_error("pdx_fd_laplace: DIFF required"); return 1; }
+    if (lap_kind == PDX_LAP_CONV && ndim == 2) { set_error("pdx_fd_laplace: the conv operator is 3-D only"); return 1; }
+    pdx_fd_desc d;
+    pdx_fd_desc_init(&d);
+    d.ndim = ndim; d.nx = nx; d.ny = ny; d.nz = nz; d.dx = dx; d.dy = dy; d.dz = dz;
+    d.lap_kind = lap_kind; d.math_mode = math_mode; d.model = PDX_MODEL_NONE;
+    d.x_begin = 0; d.x_end = nx; d.x_clamp_lo = 0; d.x_clamp_hi = nx - 1;
+    FdArgs a;
+    fill_args(d, &a);
+    a.yclo = 0; a.ychi = ny - 1; a.zclo = 0; a.zchi = nz - 1;   // pure symmetric pad, no enforce_boundary
+    a.dxlo = 0; a.dxhi = nx - 1;
+    a.Uin = X0; a.Uout = out; a.DIFF = DIFF;
+    return launch_fd_laplace_only(lap_kind, math_mode, a, (cudaStream_t)stream);
+}
+
+int pdx_fd_enforce_boundary(int ndim, int nx, int ny, int nz, int dirichlet, float value, const float* X, float* out,
+                            void* stream) {
+    if (!X || !out || X == out) { set_error("pdx_fd_enforce_boundary: need distinct non-null arrays"); return 1; }
+    if ((ndim != 2 && ndim != 3) || (ndim == 2 && nx != 1) || ny < 3 || nz < 3 || (ndim == 3 && nx < 3)) {
+        set_error("pdx_fd_enforce_boundary: bad shape");
+        return 1;
+    }
+    pdx_fd_desc d;
+    pdx_fd_desc_init(&d);
+    d.ndim = ndim; d.nx = nx; d.ny = ny; d.nz = nz;
+    d.x_begin = 0; d.x_end = nx;
+    d.x_clamp_lo = ndim == 3 ? 1 : 0; d.x_clamp_hi = ndim == 3 ? nx - 2 : 0;
+    d.dirichlet = dirichlet; d.dirichlet_value = value;
+    FdArgs a;
+    fill_args(d, &a);
+    if (ndim == 2) { a.xclo = 0; a.xchi = 0; }
+    a.Uin = X; a.Uout = out;
+    return launch_enforce_boundary(a, (cudaStream_t)stream);
+}
+
+int pdx_ionic_step(int model, int math_mode, const float* params, const float* const* param_arrays, int64_t n,
+                   const float* U, float* const* states, float* dU_out, float dt, const float* I0, float* rhs0_out,
+                   void* stream) {
+    if (!params || !U || !states || n < 0) { set_error("pdx_ionic_step: bad arguments"); return 1; }
+    if (n == 0) return 0;
+    return launch_ionic(model, math_mode, params, param_arrays, n, U, states, dU_out, dt, I0, rhs0_out,
+                        (cudaStream_t)stream);
+}
+
+int pdx_stim_apply(float* U, const float* mask, float intensity, int64_t n, void* stream) {
+    if (!U || !mask || n < 0) { set_error("pdx_stim_apply: bad arguments"); return 1; }
+    if (n == 0) return 0;
+    return launch_stim(U, mask, intensity, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,355 @@
+// pdx_fd_tma.cu - fused FD step for sm_100a: TMA-staged shared-memory tiles, march along
+// the slowest axis, stencil + ionic update + Euler update in one pass.
+//
+// Work decomposition
+//   CTA  = one (TY x 128) tile of the (y,z) plane marched over x_chunk planes.
+//   warp = R consecutive rows of the tile; lane = 4 consecutive z nodes (float4).
+// Data movement per node-step (Fenton-Karma): U is read once through TMA
+// (cp.async.bulk.tensor.3d, box = 1 x (TY+2) x (128+8) including the halo, zero-filled
+// outside the array) into a ring of NSTAGE shared-memory plane slots guarded by mbarriers;
+// V,W,S are read and written once with 128-bit global accesses (prefetched one plane
+// ahead in registers); U' is written once with 128-bit stores.  Halo re-reads hit L2.
+// The clamp-index boundary rule (enforce_boundary + symmetric pad) is applied
+// when reading shared memory: plane/row indices are clamped before addressing, z edges are
+// patched in registers (only in tiles that touch the boundary).
+#include "pdx_internal.h"
+
+namespace pdx {
+
+namespace {
+
+constexpr int TZ = 128;              // tile extent along z (contiguous axis)
+constexpr int ZH = 4;                // z halo per side in floats (keeps 16-byte alignment)
+constexpr int COLS = TZ + 2 * ZH;    // 136 floats per smem row
+constexpr int NWARP = 8;
+constexpr int NTHREADS = NWARP * 32;
+constexpr int STAGES = 6;            // ring depth (3 planes in use + 3 in flight)
+
+constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <int R, bool HET>
+struct Geo {
+    static constexpr int TY = NWARP * R;
+    static constexpr int ROWS = TY + 2;
+    static constexpr int FIELD_BYTES = round_up(ROWS * COLS * 4, 128);
+    static constexpr int SLOT_BYTES = FIELD_BYTES * (HET ? 2 : 1);
+    static constexpr int TX_BYTES = ROWS * COLS * 4 * (HET ? 2 : 1);
+    static constexpr int SMEM_BYTES = STAGES * SLOT_BYTES + STAGES * 8;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA: 3-D tiled bulk tensor load global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+struct F4 {
+    float v[4];
+};
+__device__ __forceinline__ F4 lds4(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ F4 ldg4(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void stg4(float* p, const F4& a) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+// z-edge patch of the four centre columns of a row (index clamp to [zclo, zchi])
+__device__ __forceinline__ void zfix(F4& a, bool lo2, bool hi2) {
+    if (lo2) a.v[0] = a.v[1];
+    if (hi2) a.v[3] = a.v[2];
+}
+
+template <int MODEL, bool HET, int MATH, bool HAS_X, int R>
+__global__ void __launch_bounds__(NTHREADS, (R == 1 && !HET) ? 3 : 2)
+fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD,
+              const __grid_constant__ FdArgs a) {
+    using G = Geo<R, HET>;
+    constexpr int NS = NStates<MODEL>::value;
+    constexpr int TY = G::TY;
+    constexpr int NSTAGE = STAGES;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * G::SLOT_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int b = blockIdx.x;
+    const int tz = b % a.ntz;  b /= a.ntz;
+    const int ty = b % a.nty;  b /= a.nty;
+    const int z0 = tz * TZ, y0 = ty * TY;
+    const int xb = a.xb + b * a.x_chunk;
+    const int xe = min(xb + a.x_chunk, a.xe);
+    const int np = xe - xb;
+    const int nlog = HAS_X ? np + 2 : np;           // logical planes q = xb-1 .. xe (3-D)
+    const int q0 = HAS_X ? xb - 1 : xb;
+
+    auto slotU = [&](int j) { return reinterpret_cast<float*>(smem + (j % NSTAGE) * G::SLOT_BYTES); };
+    auto slotD = [&](int j) { return reinterpret_cast<float*>(smem + (j % NSTAGE) * G::SLOT_BYTES + G::FIELD_BYTES); };
+    auto issue = [&](int j) {   // thread 0 only
+        const int q = q0 + j;
+        uint64_t* bar = &full[j % NSTAGE];
+        mbar_expect_tx(bar, G::TX_BYTES);
+        tma_load_3d(slotU(j), &mapU, z0 - ZH, y0 - 1, HAS_X ? clampi(q, a.xclo, a.xchi) : q, bar);
+        if (HET) tma_load_3d(slotD(j), &mapD, z0 - ZH, y0 - 1, HAS_X ? clampi(q, a.dxlo, a.dxhi) : q, bar);
+    };
+    auto wait_plane = [&](int j) { mbar_wait(&full[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1)); };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int n0 = min(NSTAGE, nlog);
+        for (int j = 0; j < n0; ++j) issue(j);
+    }
+
+    // ---- per-thread geometry (constant along the march) ----
+    const int  z    = z0 + 4 * lane;
+    const int  col  = ZH + 4 * lane;
+    const bool zact = z < a.nz;
+    const bool zb_tile = (z0 - 1 < a.zclo) || (z0 + TZ > a.zchi);            // CTA uniform
+    const bool yb_tile = (y0 - 1 < a.yclo) || (y0 + TY > a.ychi);            // CTA uniform
+    const bool lo2 = z < a.zclo, lo1 = z - 1 < a.zclo;
+    const bool hi2 = z + 3 > a.zchi, hi1 = z + 4 > a.zchi;
+    const bool dlo1 = z - 1 < 0, dhi1 = z + 4 > a.nz - 1;                    // DIFF: symmetric pad only
+
+    int  gy[R], rc[R], rm[R], rp[R], drm[R], drp[R];
+    bool act[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        gy[r]  = y0 + warp * R + r;
+        act[r] = zact && gy[r] < a.ny;
+        const int g = min(gy[r], a.ny - 1);          // keep inactive rows addressable
+        rc[r]  = (clampi(g, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
+        rm[r]  = (clampi(g - 1, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
+        rp[r]  = (clampi(g + 1, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
+        drm[r] = (max(g - 1, 0) - (y0 - 1)) * COLS + col;
+        drp[r] = (min(g + 1, a.ny - 1) - (y0 - 1)) * COLS + col;
+    }
+    const int drc0 = (0 - (y0 - 1)) * COLS + col;    // + g*COLS gives the unclamped DIFF row
+
+    // ---- state prefetch registers ----
+    F4 stn[R][NS > 0 ? NS : 1];
+    auto load_states = [&](int p) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!act[r]) continue;
+            const size_t gi = ((size_t)p * a.ny + gy[r]) * a.nz + z;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) stn[r][s] = ldg4(a.st[s] + gi);
+        }
+    };
+    if (NS > 0 && np > 0) load_states(xb);
+
+    for (int i = 0; i < np; ++i) {
+        const int p = xb + i;
+        const int jc = HAS_X ? i + 1 : i;
+        if (HAS_X) {
+            if (i == 0) { wait_plane(0); wait_plane(1); }
+            wait_plane(i + 2);
+        } else {
+            wait_plane(i);
+        }
+        const float* Sc = slotU(jc);
+        const float* Sm = HAS_X ? slotU(jc - 1) : Sc;
+        const float* Sp = HAS_X ? slotU(jc + 1) : Sc;
+        const bool raw_diff = yb_tile || zb_tile || (HAS_X && (p < a.xclo || p > a.xchi));   // CTA uniform
+
+        F4 stc[R][NS > 0 ? NS : 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) stc[r][s] = stn[r][s];
+        if (NS > 0 && i + 1 < np) load_states(p + 1);
+
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!act[r]) continue;
+            const size_t gi = ((size_t)p * a.ny + gy[r]) * a.nz + z;
+            F4 c = lds4(Sc + rc[r]);
+            float zl = Sc[rc[r] - 1], zr = Sc[rc[r] + 4];
+            F4 ym = lds4(Sc + rm[r]), yp = lds4(Sc + rp[r]);
+            F4 xm, xp;
+            if (HAS_X) { xm = lds4(Sm + rc[r]); xp = lds4(Sp + rc[r]); }
+            F4 raw = c;
+            if (raw_diff) {
+                if (MODEL != PDX_MODEL_NONE) raw = ldg4(a.Uin + gi);
+                if (zb_tile) {
+                    zfix(c, lo2, hi2); zfix(ym, lo2, hi2); zfix(yp, lo2, hi2);
+                    if (HAS_X) { zfix(xm, lo2, hi2); zfix(xp, lo2, hi2); }
+                    zl = lo1 ? c.v[0] : zl;          // after zfix c.v[0] already holds the clamped value
+                    zr = hi1 ? c.v[3] : zr;
+                }
+            }
+            F4 dc, dym, dyp, dxm, dxp;
+            float dzl = 0.f, dzr = 0.f;
+            if (HET) {
+                const float* Dc = slotD(jc);
+                const int drc = drc0 + min(gy[r], a.ny - 1) * COLS;
+                dc = lds4(Dc + drc);
+                dzl = dlo1 ? dc.v[0] : Dc[drc - 1];
+                dzr = dhi1 ? dc.v[3] : Dc[drc + 4];
+                dym = lds4(Dc + drm[r]); dyp = lds4(Dc + drp[r]);
+                if (HAS_X) { dxm = lds4(slotD(jc - 1) + drc); dxp = lds4(slotD(jc + 1) + drc); }
+            }
+            F4 out;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float cc = c.v[e];
+                const float zm_ = e == 0 ? zl : c.v[e - 1];
+                const float zp_ = e == 3 ? zr : c.v[e + 1];
+                float lap;
+                if (HET) {
+                    const float dcc = dc.v[e];
+                    const float dzm_ = e == 0 ? dzl : dc.v[e - 1];
+                    const float dzp_ = e == 3 ? dzr : dc.v[e + 1];
+                    lap = lap_axis_het<MATH>(ym.v[e], cc, yp.v[e], dym.v[e], dcc, dyp.v[e], a.hysq, a.rhysq);
+                    if (HAS_X)
+                        lap = madd<MATH>(lap_axis_het<MATH>(xm.v[e], cc, xp.v[e], dxm.v[e], dcc, dxp.v[e], a.hxsq,
+                                                            a.rhxsq), lap);
+                    lap = madd<MATH>(lap, lap_axis_het<MATH>(zm_, cc, zp_, dzm_, dcc, dzp_, a.hzsq, a.rhzsq));
+                } else {
+                    lap = lap_axis<MATH>(ym.v[e], cc, yp.v[e], a.hysq, a.rhysq);
+                    if (HAS_X) lap = madd<MATH>(lap_axis<MATH>(xm.v[e], cc, xp.v[e], a.hxsq, a.rhxsq), lap);
+                    lap = madd<MATH>(lap, lap_axis<MATH>(zm_, cc, zp_, a.hzsq, a.rhzsq));
+                }
+                float u1 = cc;
+                if (MODEL != PDX_MODEL_NONE) {
+                    float st[PDX_MAX_STATES];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) st[s] = stc[r][s].v[e];
+                    const float dU = ionic_update<MODEL, MATH>(raw.v[e], st, a.mp);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) stc[r][s].v[e] = st[s];
+                    u1 = madd<MATH>(u1, mmul<MATH>(a.dt, dU));
+                }
+                out.v[e] = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
+            }
+            stg4(a.Uout + gi, out);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) stg4(a.st[s] + gi, stc[r][s]);
+        }
+        __syncthreads();                              // everyone is done with logical plane i
+        if (tid == 0 && i + NSTAGE < nlog) issue(i + NSTAGE);
+    }
+}
+
+template <int MODEL, bool HET, int MATH, bool HAS_X, int R>
+int launch_inst(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
+    using G = Geo<R, HET>;
+    auto kern = fd_tma_kernel<MODEL, HET, MATH, HAS_X, R>;
+    static bool attr_done = false;   // per instantiation
+    if (!attr_done) {
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES),
+                       "cudaFuncSetAttribute(smem)"))
+            return 1;
+        attr_done = true;
+    }
+    const int nplanes = a.xe - a.xb;
+    if (nplanes <= 0) return 0;
+    const int nchunk = (nplanes + a.x_chunk - 1) / a.x_chunk;
+    const long long nb = (long long)a.ntz * a.nty * nchunk;
+    if (nb > 0x7fffffffLL) { set_error("fd_tma: grid too large"); return 1; }
+    kern<<<(unsigned)nb, NTHREADS, G::SMEM_BYTES, s>>>(mU, mD, a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "fd_tma_kernel launch");
+}
+
+template <int MODEL, bool HET, int MATH>
+int launch_hasx(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
+    return a.has_x ? launch_inst<MODEL, HET, MATH, true, 1>(a, mU, mD, s)
+                   : launch_inst<MODEL, HET, MATH, false, 1>(a, mU, mD, s);
+}
+template <int MODEL, bool HET>
+int launch_math(int math, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
+    return math == PDX_MATH_EXACT ? launch_hasx<MODEL, HET, PDX_MATH_EXACT>(a, mU, mD, s)
+                                  : launch_hasx<MODEL, HET, PDX_MATH_FAST>(a, mU, mD, s);
+}
+template <int MODEL>
+int launch_het(bool het, int math, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
+    return het ? launch_math<MODEL, true>(math, a, mU, mD, s) : launch_math<MODEL, false>(math, a, mU, mD, s);
+}
+
+}  // namespace
+
+bool fd_tma_supported(const pdx_fd_desc& d) {
+    if (d.nz % 4 != 0 || d.nz < 4) return false;
+    if (d.dirichlet) return false;
+    if (d.lap_kind == PDX_LAP_CONV && d.math_mode == PDX_MATH_EXACT) return false;   // different rounding order
+    if (d.ny < 3) return false;
+    return true;
+}
+
+void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* box_y, int* box_z) {
+    (void)d;
+    *tile_y = NWARP * 1;
+    *tile_z = TZ;
+    *box_y  = NWARP * 1 + 2;
+    *box_z  = COLS;
+}
+
+int fd_tma_auto_chunk(const pdx_fd_desc& d) {
+    // enough CTAs for >= ~10 waves of 148 SMs x 3 CTAs, but at least 8 planes per CTA so the
+    // two extra halo planes per chunk stay a small fraction of the U traffic
+    const int nplanes = d.x_end - d.x_begin;
+    if (d.ndim == 2 || nplanes <= 1) return 1;
+    const long long tiles = (long long)((d.ny + NWARP - 1) / NWARP) * ((d.nz + TZ - 1) / TZ);
+    const long long want = 148LL * 3 * 10;
+    long long nchunk = (want + tiles - 1) / tiles;
+    if (nchunk < 1) nchunk = 1;
+    int chunk = (int)((nplanes + nchunk - 1) / nchunk);
+    if (chunk < 8) chunk = 8;
+    if (chunk > nplanes) chunk = nplanes;
+    return chunk;
+}
+
+int launch_fd_tma(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD,
+                  cudaStream_t s) {
+    const bool het = d.lap_kind == PDX_LAP_HETEROG;
+    switch (d.model) {
+        case PDX_MODEL_NONE:     return launch_het<PDX_MODEL_NONE>(het, d.math_mode, a, mU, mD, s);
+        case PDX_MODEL_FENTON4V: return launch_het<PDX_MODEL_FENTON4V>(het, d.math_mode, a, mU, mD, s);
+        case PDX_MODEL_MMS2V:    return launch_het<PDX_MODEL_MMS2V>(het, d.math_mode, a, mU, mD, s);
+        case PDX_MODEL_MS2V:     return launch_het<PDX_MODEL_MS2V>(het, d.math_mode, a, mU, mD, s);
+    }
+    set_error("unknown model");
+    return 1;
+}
+
+}  // namespace pdx

@@ -1,0 +1,388 @@
+// pdx_fem.cu - FEM side of the hot path: CSR SpMV, Jacobi-PCG as one persistent
+// cooperative kernel, and the explicit mass-lumped step fused with the ionic update.
+//
+// Reference call sites: tf.raw_ops.SparseMatrixMatMul (linearsolvers/conjgrad.py:99-101,
+// physics/monodomainSolver.py:104), ConjGrad._initialize/_iterate/solve
+// (conjgrad.py:172-203,257-312), JacobiPrecond.solve_precond_system (jacobi_precond.py:35-41).
+#include <cooperative_groups.h>
+#include <new>
+#include "pdx_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace pdx {
+namespace {
+
+// ---------------------------------------------------------------- SpMV
+// G lanes cooperate on one row (G chosen from the mean row length).
+template <int G>
+__device__ __forceinline__ float row_dot(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                         const float* x, int beg, int end, int sub, bool cg_loads) {
+    float acc = 0.0f;
+    for (int k = beg + sub; k < end; k += G) {
+        const float xv = cg_loads ? __ldcg(x + col[k]) : x[col[k]];
+        acc = fmaf(val[k], xv, acc);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
+    return acc;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) spmv_kernel(int n, const int32_t* __restrict__ rowptr,
+                                                   const int32_t* __restrict__ col, const float* __restrict__ val,
+                                                   const float* __restrict__ x, float* __restrict__ y) {
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int sub = threadIdx.x % G;
+    const int ngroups = gridDim.x * blockDim.x / G;
+    const int nround = (n + ngroups - 1) / ngroups * ngroups;   // all lanes reach the shuffles
+    for (int row = gid; row < nround; row += ngroups) {
+        const bool valid = row < n;
+        const float acc = row_dot<G>(col, val, x, valid ? rowptr[row] : 0, valid ? rowptr[row + 1] : 0, sub, false);
+        if (valid && sub == 0) y[row] = acc;
+    }
+}
+
+int pick_group(int n, int64_t nnz) {
+    const double mean = n > 0 ? (double)nnz / n : 1.0;
+    if (mean <= 6) return 4;
+    if (mean <= 12) return 8;
+    if (mean <= 24) return 16;
+    return 32;
+}
+
+// ---------------------------------------------------------------- PCG (cooperative)
+struct PcgArgs {
+    int n;
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* val;
+    const float* minv;      // may be null
+    const float* b;
+    float* x;
+    float *r, *p, *q;       // work vectors
+    float* part;            // 3 * gridDim.x partial sums
+    int maxiter;
+    int check_every;
+    double toll_sq;
+    int32_t* info;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float t = 0.0f;
+    const int nw = blockDim.x >> 5;
+    if (w == 0) {
+        t = lane < nw ? sh[lane] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// Sum of the per-block partials, same order in every block => every block gets the same bits.
+__device__ __forceinline__ float grid_total(const float* part, float* sh) {
+    float v = 0.0f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(part + i);
+    return block_sum(v, sh);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float sh[33];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const int gid = tid / G, sub = threadIdx.x % G, ngroups = nthreads / G;
+    const int nb = gridDim.x;
+    float* part_pq = a.part;
+    float* part_rr = a.part + nb;
+    float* part_rz = a.part + 2 * nb;
+    const int nround = (a.n + ngroups - 1) / ngroups * ngroups;   // keep groups converged for shuffles
+
+    // r = b - A x ; z = Minv r ; p = z ; rz = r.z          (conjgrad.py:191-203)
+    float loc_rz = 0.0f, loc_rr = 0.0f;
+    for (int row = gid; row < nround; row += ngroups) {
+        {
+            const bool valid = row < a.n;
+            const float ax = row_dot<G>(a.col, a.val, a.x, valid ? a.rowptr[row] : 0, valid ? a.rowptr[row + 1] : 0,
+                                        sub, true);
+            if (valid && sub == 0) {
+                const float r = __fsub_rn(a.b[row], ax);
+                const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
+                __stcg(a.r + row, r);
+                __stcg(a.p + row, z);
+                loc_rz = fmaf(r, z, loc_rz);
+                loc_rr = fmaf(r, r, loc_rr);
+            }
+        }
+    }
+    float v = block_sum(loc_rz, sh);
+    float w = block_sum(loc_rr, sh);
+    if (threadIdx.x == 0) { __stcg(part_rz + blockIdx.x, v); __stcg(part_rr + blockIdx.x, w); }
+    grid.sync();
+    float rz = grid_total(part_rz, sh);
+    float res = grid_total(part_rr, sh);
+
+    int niters = 0;
+    int flags = 0;
+    for (int k = 1; k <= a.maxiter; ++k) {
+        niters = k;
+        // q = A p ; pq = p.q
+        float loc_pq = 0.0f;
+        for (int row = gid; row < nround; row += ngroups) {
+            {
+                const bool valid = row < a.n;
+                const float ap = row_dot<G>(a.col, a.val, a.p, valid ? a.rowptr[row] : 0,
+                                            valid ? a.rowptr[row + 1] : 0, sub, true);
+                if (valid && sub == 0) {
+                    __stcg(a.q + row, ap);
+                    loc_pq = fmaf(__ldcg(a.p + row), ap, loc_pq);
+                }
+            }
+        }
+        v = block_sum(loc_pq, sh);
+        if (threadIdx.x == 0) __stcg(part_pq + blockIdx.x, v);
+        grid.sync();
+        const float pq = grid_total(part_pq, sh);
+        const float alpha = rz / pq;
+        // x += alpha p ; r -= alpha q ; res = r.r ; z = Minv r ; rz' = r.z   (conjgrad.py:172-183)
+        loc_rz = 0.0f; loc_rr = 0.0f;
+        for (int i = tid; i < a.n; i += nthreads) {
+            const float pi = __ldcg(a.p + i);
+            __stcg(a.x + i, fmaf(alpha, pi, __ldcg(a.x + i)));
+            const float r = fmaf(-alpha, __ldcg(a.q + i), __ldcg(a.r + i));
+            __stcg(a.r + i, r);
+            const float z = a.minv ? a.minv[i] * r : r;
+            loc_rr = fmaf(r, r, loc_rr);
+            loc_rz = fmaf(r, z, loc_rz);
+        }
+        v = block_sum(loc_rz, sh);
+        w = block_sum(loc_rr, sh);
+        if (threadIdx.x == 0) { __stcg(part_rz + blockIdx.x, v); __stcg(part_rr + blockIdx.x, w); }
+        grid.sync();
+        const float rznew = grid_total(part_rz, sh);
+        res = grid_total(part_rr, sh);
+        const float beta = rznew / rz;
+        // p = z + beta p
+        for (int i = tid; i < a.n; i += nthreads) {
+            const float r = __ldcg(a.r + i);
+            const float z = a.minv ? a.minv[i] * r : r;
+            __stcg(a.p + i, fmaf(beta, __ldcg(a.p + i), z));
+        }
+        // batched convergence test + NaN/Inf guard (conjgrad.py:293-300)
+        if (k % a.check_every == 0) {
+            const bool finite = isfinite(res);
+            if (!finite || (double)res < a.toll_sq) {
+                if (!finite) flags |= 2;
+                break;
+            }
+        }
+        rz = rznew;
+        grid.sync();
+    }
+    if (niters >= a.maxiter) flags |= 1;
+    if (tid == 0 && a.info) {
+        a.info[0] = niters;
+        a.info[1] = __float_as_int(res);
+        a.info[2] = flags;
+        a.info[3] = 0;
+    }
+}
+
+// ---------------------------------------------------------------- explicit lumped step
+struct ExplArgs {
+    int n;
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* kval;
+    const float* mlinv;
+    const float* Uin;
+    float* Uout;
+    float* st[PDX_MAX_STATES];
+    const float* I0;
+    ModelParams mp;
+};
+
+template <int MODEL, int MATH, int G>
+__global__ void __launch_bounds__(256) fem_explicit_kernel(const __grid_constant__ ExplArgs a) {
+    constexpr int NS = NStates<MODEL>::value;
+    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int sub = threadIdx.x % G;
+    const int ngroups = gridDim.x * blockDim.x / G;
+    const int nround = (a.n + ngroups - 1) / ngroups * ngroups;
+    for (int row = gid; row < nround; row += ngroups) {
+        const bool valid = row < a.n;
+        const float ku = row_dot<G>(a.col, a.kval, a.Uin, valid ? a.rowptr[row] : 0, valid ? a.rowptr[row + 1] : 0,
+                                    sub, false);
+        if (valid && sub == 0) {
+            const float U = a.Uin[row];
+            float st[PDX_MAX_STATES];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) st[s] = a.st[s][row];
+            float dU = MODEL != PDX_MODEL_NONE ? ionic_update<MODEL, MATH>(U, st, a.mp) : 0.0f;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) a.st[s][row] = st[s];
+            if (a.I0) dU += a.I0[row];
+            // U1 = U + dt*(dU + I0) - dt*mlinv*(K U)
+            a.Uout[row] = fmaf(-a.mp.dt * a.mlinv[row], ku, fmaf(a.mp.dt, dU, U));
+        }
+    }
+}
+
+template <int MODEL, int MATH>
+int launch_expl(int G, const ExplArgs& a, unsigned nb, cudaStream_t s) {
+    switch (G) {
+        case 4:  fem_explicit_kernel<MODEL, MATH, 4><<<nb, 256, 0, s>>>(a); break;
+        case 8:  fem_explicit_kernel<MODEL, MATH, 8><<<nb, 256, 0, s>>>(a); break;
+        case 16: fem_explicit_kernel<MODEL, MATH, 16><<<nb, 256, 0, s>>>(a); break;
+        default: fem_explicit_kernel<MODEL, MATH, 32><<<nb, 256, 0, s>>>(a); break;
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "fem_explicit_kernel launch");
+}
+
+}  // namespace
+}  // namespace pdx
+
+using namespace pdx;
+
+struct pdx_pcg {
+    int n;
+    int64_t nnz;
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* val;
+    const float* minv;
+    float* work;      // r, p, q
+    float* part;
+    int G;
+    int nblocks;
+};
+
+extern "C" {
+
+int pdx_csr_spmv(int32_t n, const int32_t* rowptr, const int32_t* col, const float* val, const float* x, float* y,
+                 void* stream) {
+    if (n < 0 || !rowptr || !col || !val || !x || !y) { set_error("pdx_csr_spmv: bad arguments"); return 1; }
+    if (n == 0) return 0;
+    // group size from a cheap upper bound: read nnz lazily is a device sync, so use 8 lanes
+    // (P1 triangle/tet meshes have 7-15 entries per row)
+    constexpr int G = 8;
+    long long threads = (long long)n * G;
+    long long nb = (threads + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    // round rows per pass so that groups stay converged: handled by the kernel loop bound (row < n)
+    spmv_kernel<G><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(n, rowptr, col, val, x, y);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "spmv_kernel launch");
+}
+
+int pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const float* val, const float* minv,
+                   pdx_pcg** out) {
+    if (n <= 0 || !rowptr || !col || !val || !out) { set_error("pdx_pcg_create: bad arguments"); return 1; }
+    pdx_pcg* s = new (std::nothrow) pdx_pcg();
+    if (!s) { set_error("out of memory"); return 1; }
+    s->n = n; s->rowptr = rowptr; s->col = col; s->val = val; s->minv = minv;
+    int32_t last = 0;
+    if (check_cuda(cudaMemcpy(&last, rowptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost), "read nnz")) { delete s; return 1; }
+    s->nnz = last;
+    s->G = pick_group(n, s->nnz);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 0;
+    cudaError_t e;
+    switch (s->G) {
+        case 4:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<4>, 256, 0); break;
+        case 8:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<8>, 256, 0); break;
+        case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<16>, 256, 0); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<32>, 256, 0); break;
+    }
+    if (check_cuda(e, "occupancy query") || per_sm < 1) { delete s; if (per_sm < 1) set_error("pcg kernel cannot be resident"); return 1; }
+    // small systems are latency bound: one block per SM keeps the grid barrier cheap
+    long long want = ((long long)n * s->G + 255) / 256;
+    long long cap = (long long)sms * (per_sm > 4 ? 4 : per_sm);
+    long long nb = want < cap ? want : cap;
+    if (nb < 1) nb = 1;
+    if (nb > sms && (long long)n * s->G <= (long long)sms * 256 * 8) nb = sms;
+    s->nblocks = (int)nb;
+    if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 3 * (size_t)n), "cudaMalloc(pcg work)")) { delete s; return 1; }
+    if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 3 * (size_t)s->nblocks), "cudaMalloc(pcg partials)")) {
+        cudaFree(s->work); delete s; return 1;
+    }
+    *out = s;
+    return 0;
+}
+
+void pdx_pcg_destroy(pdx_pcg* s) {
+    if (!s) return;
+    cudaFree(s->work);
+    cudaFree(s->part);
+    delete s;
+}
+
+int pdx_pcg_solve(pdx_pcg* s, const float* b, float* x, int maxiter, double toll, int check_every, int32_t* info,
+                  void* stream) {
+    if (!s || !b || !x || maxiter < 0) { set_error("pdx_pcg_solve: bad arguments"); return 1; }
+    PcgArgs a{};
+    a.n = s->n; a.rowptr = s->rowptr; a.col = s->col; a.val = s->val; a.minv = s->minv;
+    a.b = b; a.x = x;
+    a.r = s->work; a.p = s->work + s->n; a.q = s->work + 2 * (size_t)s->n;
+    a.part = s->part;
+    a.maxiter = maxiter;
+    a.check_every = check_every > 0 ? check_every : 1;
+    a.toll_sq = toll * toll;
+    a.info = info;
+    void* args[] = {&a};
+    const void* fn;
+    switch (s->G) {
+        case 4:  fn = (const void*)pcg_kernel<4>; break;
+        case 8:  fn = (const void*)pcg_kernel<8>; break;
+        case 16: fn = (const void*)pcg_kernel<16>; break;
+        default: fn = (const void*)pcg_kernel<32>; break;
+    }
+    count_launch();
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(s->nblocks), dim3(256), args, 0, (cudaStream_t)stream),
+                      "pcg_kernel cooperative launch");
+}
+
+int pdx_fem_explicit_step(int model, int math_mode, const float* params, int32_t n, const int32_t* rowptr,
+                          const int32_t* col, const float* kval, const float* mlinv, const float* U_in, float* U_out,
+                          float* const* states, const float* I0, float dt, void* stream) {
+    if (n <= 0 || !rowptr || !col || !kval || !mlinv || !U_in || !U_out || U_in == U_out) {
+        set_error("pdx_fem_explicit_step: bad arguments");
+        return 1;
+    }
+    const int ns = pdx_model_num_states(model);
+    if (ns < 0 || (ns > 0 && (!states || !params))) { set_error("pdx_fem_explicit_step: bad model/states"); return 1; }
+    ExplArgs a{};
+    a.n = n; a.rowptr = rowptr; a.col = col; a.kval = kval; a.mlinv = mlinv; a.Uin = U_in; a.Uout = U_out; a.I0 = I0;
+    for (int i = 0; i < ns; ++i) a.st[i] = states[i];
+    if (ns > 0) fill_model_params(model, params, dt, &a.mp); else a.mp.dt = dt;
+    constexpr int G = 8;
+    long long nb = ((long long)n * G + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool ex = math_mode == PDX_MATH_EXACT;
+    switch (model) {
+        case PDX_MODEL_NONE:     return launch_expl<PDX_MODEL_NONE, PDX_MATH_FAST>(G, a, (unsigned)nb, s);
+        case PDX_MODEL_FENTON4V: return ex ? launch_expl<PDX_MODEL_FENTON4V, PDX_MATH_EXACT>(G, a, (unsigned)nb, s)
+                                           : launch_expl<PDX_MODEL_FENTON4V, PDX_MATH_FAST>(G, a, (unsigned)nb, s);
+        case PDX_MODEL_MMS2V:    return ex ? launch_expl<PDX_MODEL_MMS2V, PDX_MATH_EXACT>(G, a, (unsigned)nb, s)
+                                           : launch_expl<PDX_MODEL_MMS2V, PDX_MATH_FAST>(G, a, (unsigned)nb, s);
+        case PDX_MODEL_MS2V:     return ex ? launch_expl<PDX_MODEL_MS2V, PDX_MATH_EXACT>(G, a, (unsigned)nb, s)
+                                           : launch_expl<PDX_MODEL_MS2V, PDX_MATH_FAST>(G, a, (unsigned)nb, s);
+    }
+    set_error("pdx_fem_explicit_step: unknown model");
+    return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// pdx_internal.h - host/device structs shared by the translation units of libpdx.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/pdx.h"
+#include "pdx_math.cuh"
+
+namespace pdx {
+
+// Arguments of one fused FD step launch (by value, __grid_constant__).
+struct FdArgs {
+    const float* Uin;
+    float*       Uout;
+    float*       st[PDX_MAX_STATES];
+    const float* DIFF;
+    int nx, ny, nz;
+    int xb, xe;                  // planes advanced
+    int xclo, xchi;              // clamp of stencil plane indices for U (enforce_boundary + pad)
+    int yclo, ychi, zclo, zchi;  // same for the y / z axes
+    int dxlo, dxhi;              // clamp of plane indices for DIFF (symmetric pad only)
+    int x_chunk;                 // planes per CTA (TMA kernel)
+    int ntz, nty;                // tile counts (TMA kernel)
+    int has_x;                   // 0 for 2-D fields
+    int dirichlet;
+    float dirichlet_value;
+    float dt, coef;
+    float hxsq, hysq, hzsq;      // dx*dx ... (fp32 products)
+    float rhxsq, rhysq, rhzsq;   // reciprocals (FAST)
+    float kx, ky, kz, kc;        // conv-kernel taps (CONV): see laplace_convolution...py:30-40
+    ModelParams mp;
+};
+
+void set_error(const std::string& msg);
+int  check_cuda(cudaError_t e, const char* what);
+void count_launch(int64_t n = 1);
+
+void fill_model_params(int model, const float* params, float dt, ModelParams* out);
+
+// generic (any shape, 2-D/3-D, every operator/model) fused step
+int launch_fd_generic(const pdx_fd_desc& d, const FdArgs& a, cudaStream_t s);
+int launch_fd_laplace_only(int lap_kind, int math_mode, const FdArgs& a, cudaStream_t s);
+int launch_enforce_boundary(const FdArgs& a, cudaStream_t s);
+int launch_ionic(int model, int math, const float* params, const float* const* parr, int64_t n, const float* U,
+                 float* const* states, float* dU, float dt, const float* I0, float* rhs0, cudaStream_t s);
+int launch_stim(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s);
+// TMA-staged tile kernel: requires nz % 4 == 0, 16-byte aligned arrays, HOMOG/HETEROG
+bool fd_tma_supported(const pdx_fd_desc& d);
+int  launch_fd_tma(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mapU, const CUtensorMap& mapD,
+                   cudaStream_t s);
+int  make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int nz, int box_x, int box_y,
+                        int box_z);
+// geometry of the TMA kernel's tile, needed by the host to build the tensor maps
+void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* box_y, int* box_z);
+int  fd_tma_auto_chunk(const pdx_fd_desc& d);
+
+}  // namespace pdx

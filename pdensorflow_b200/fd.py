@@ -1,0 +1,303 @@
+"""Fused explicit finite-difference monodomain stepping on B200 (host side).
+
+``FDStepper`` owns the device buffers of one grid (or one slab of a distributed grid) and
+drives ``pdx_fd_step``: one kernel launch per time step that fuses what the reference
+examples' ``solve()`` spreads over ~150 TensorFlow ops (Tests/FD/Fenton/fenton.py:90-99:
+enforce_boundary + differentiate + laplace + Euler update).  ``run()`` replays a
+CUDA-graph-captured block of steps instead of the reference's Python per-step loop
+(fenton.py:150-159).
+
+``SlabPartition``/``DistributedFDStepper`` split the slowest axis (reference axis 0) over
+the ranks of a torch.distributed group; one plane of U is exchanged per neighbour per step
+(NCCL send/recv over NVLink), overlapped with the interior planes.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_MODEL_IDS = {None: L.MODEL_NONE, 'none': L.MODEL_NONE, 'heat': L.MODEL_NONE,
+              'fenton4v': L.MODEL_FENTON4V, 'mms2v': L.MODEL_MMS2V, 'ms2v': L.MODEL_MS2V}
+_LAP_IDS = {'homog': L.LAP_HOMOG, 'conv': L.LAP_CONV, 'heterog': L.LAP_HETEROG}
+_MATH_IDS = {'exact': L.MATH_EXACT, 'fast': L.MATH_FAST}
+_KERNEL_IDS = {'auto': L.KERNEL_AUTO, 'generic': L.KERNEL_GENERIC, 'tma': L.KERNEL_TMA}
+STATE_INIT = {L.MODEL_FENTON4V: (1.0, 1.0, 0.0), L.MODEL_MMS2V: (1.0,), L.MODEL_MS2V: (1.0,), L.MODEL_NONE: ()}
+
+
+class SlabPartition:
+    """Contiguous split of the slowest axis (NX planes) over ``world`` ranks.
+
+    Local arrays carry one ghost plane per side (array plane 0 and nloc+1); global plane g
+    lives at array plane g - x0 + 1.  Stencil plane indices are clamped to the image of the
+    global range [1, NX-2] (enforce_boundary + symmetric pad), which is a no-op on interior
+    ranks whose ghost planes hold the neighbours' data.
+    """
+
+    def __init__(self, NX, rank=0, world=1):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError('bad rank/world')
+        if NX < 3 * world:
+            raise ValueError('need at least 3 planes per rank')
+        base, rem = divmod(NX, world)
+        self.NX, self.rank, self.world = NX, rank, world
+        self.x0 = rank * base + min(rank, rem)
+        self.nloc = base + (1 if rank < rem else 0)
+        self.x1 = self.x0 + self.nloc
+        self.nx_array = self.nloc + 2
+        self.x_begin, self.x_end = 1, self.nloc + 1
+        self.x_clamp_lo = max(1 - self.x0 + 1, 0)
+        self.x_clamp_hi = min(NX - 2 - self.x0 + 1, self.nloc + 1)
+        self.lo_rank = rank - 1 if rank > 0 else None
+        self.hi_rank = rank + 1 if rank < world - 1 else None
+
+    def scatter(self, G):
+        """Local array (with ghost planes filled from the global field) of a global array."""
+        loc = np.zeros((self.nx_array,) + tuple(G.shape[1:]), dtype=G.dtype)
+        lo, hi = max(self.x0 - 1, 0), min(self.x1 + 1, self.NX)
+        loc[lo - self.x0 + 1: hi - self.x0 + 1] = G[lo:hi]
+        return loc
+
+    def owned(self, loc):
+        return loc[1:self.nloc + 1]
+
+
+def exchange_halos(U, part, group=None):
+    """Fill the ghost planes of local array ``U`` from the neighbouring ranks.
+
+    Array plane 1 goes to the lower neighbour's ghost plane nloc+1, array plane nloc to the
+    upper neighbour's ghost plane 0.  Works on CUDA (NCCL) and CPU (gloo) tensors.
+    Returns the list of outstanding work handles (already waited for gloo).
+    """
+    import torch.distributed as dist
+    ops = []
+    if part.lo_rank is not None:
+        ops.append(dist.P2POp(dist.isend, U[1], part.lo_rank, group))
+        ops.append(dist.P2POp(dist.irecv, U[0], part.lo_rank, group))
+    if part.hi_rank is not None:
+        ops.append(dist.P2POp(dist.isend, U[part.nloc], part.hi_rank, group))
+        ops.append(dist.P2POp(dist.irecv, U[part.nloc + 1], part.hi_rank, group))
+    if not ops:
+        return []
+    reqs = dist.batch_isend_irecv(ops)
+    for r in reqs:
+        r.wait()          # NCCL: stream-orders the current stream after the transfer
+    return reqs
+
+
+class FDStepper:
+    """One grid (or slab) advanced by the fused kernel.
+
+    shape:    (W, H, D) or (W, H): the reference's array layout (last axis contiguous)
+    spacing:  (DX, DY, DZ) or (DX, DY)
+    dt, diff: Python floats as in the examples' config (fenton.py:170-183); the
+              coefficient f32(diff*dt) is formed in float64 first, like the reference does
+    model:    'fenton4v' | 'mms2v' | 'ms2v' | None (heat equation)
+    lap:      'homog' | 'conv' | 'heterog' (then DIFF is required and carries the diffusivity)
+    """
+
+    def __init__(self, shape, spacing, dt, diff=1.0, model='fenton4v', params=None, lap='homog', DIFF=None,
+                 math='fast', kernel='auto', part=None, device=None, x_chunk=0):
+        self.device = torch.device('cuda' if device is None else device)
+        if self.device.type != 'cuda':
+            raise L.PdxError('FDStepper needs a CUDA device: there is no CPU path')
+        self.ndim = len(shape)
+        if self.ndim not in (2, 3) or len(spacing) != self.ndim:
+            raise ValueError('shape/spacing must both be 2-D or 3-D')
+        self.part = part
+        self.model_id = _MODEL_IDS[model]
+        self.lap_id = _LAP_IDS[lap]
+        d = L.FdDesc()
+        L.lib().pdx_fd_desc_init(C.byref(d))
+        d.ndim = self.ndim
+        if self.ndim == 3:
+            nx = part.nx_array if part is not None else shape[0]
+            d.nx, d.ny, d.nz = nx, shape[1], shape[2]
+            d.dx, d.dy, d.dz = (float(np.float32(s)) for s in spacing)
+            if part is not None:
+                d.x_begin, d.x_end = part.x_begin, part.x_end
+                d.x_clamp_lo, d.x_clamp_hi = part.x_clamp_lo, part.x_clamp_hi
+        else:
+            if part is not None:
+                raise ValueError('slab partition is 3-D only')
+            d.nx, d.ny, d.nz = 1, shape[0], shape[1]
+            d.dy, d.dz = (float(np.float32(s)) for s in spacing)
+        self.array_shape = (d.nx, d.ny, d.nz) if self.ndim == 3 else (d.ny, d.nz)
+        d.dt = float(np.float32(dt))
+        d.coef = float(np.float32(dt)) if lap == 'heterog' else float(np.float32(float(diff) * float(dt)))
+        d.lap_kind, d.model = self.lap_id, self.model_id
+        d.math_mode, d.kernel = _MATH_IDS[math], _KERNEL_IDS[kernel]
+        d.x_chunk = int(x_chunk)
+        if self.model_id != L.MODEL_NONE:
+            p = L.default_params(self.model_id) if params is None else list(params)
+            for i, v in enumerate(p):
+                d.params[i] = float(v)
+        self.desc = d
+        handle = C.c_void_p()
+        L.check(L.lib().pdx_fd_plan_create(C.byref(d), C.byref(handle)))
+        self._plan = handle
+        self.kernel = {L.KERNEL_GENERIC: 'generic', L.KERNEL_TMA: 'tma'}[L.lib().pdx_fd_plan_kernel(handle)]
+        self.dt, self.diff = dt, diff
+        self.nstates = L.lib().pdx_model_num_states(self.model_id)
+        # buffers
+        self.Ua = torch.empty(self.array_shape, dtype=torch.float32, device=self.device)
+        self.Ub = torch.empty_like(self.Ua)
+        self.states = [torch.full(self.array_shape, v, dtype=torch.float32, device=self.device)
+                       for v in STATE_INIT[self.model_id]]
+        self.DIFF = None
+        if lap == 'heterog':
+            if DIFF is None:
+                raise ValueError("lap='heterog' needs DIFF")
+            self.DIFF = self._to_device(DIFF)
+        self._cur = 0            # 0: current U is Ua
+        self._states_arr = L.ptr_array(self.states)
+        self._graphs = {}
+        self.nsteps_done = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, '_plan', None):
+                L.lib().pdx_fd_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    # ---- data in/out -----------------------------------------------------------------
+    def _to_device(self, A):
+        if isinstance(A, torch.Tensor):
+            t = A.to(device=self.device, dtype=torch.float32)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float32)).to(self.device)
+        if self.part is not None and tuple(t.shape) != tuple(self.array_shape):
+            raise ValueError('distributed steppers take local arrays (SlabPartition.scatter)')
+        return t.reshape(self.array_shape).contiguous()
+
+    def set_U(self, U):
+        self.current_U().copy_(self._to_device(U))
+
+    def set_states(self, states):
+        for dst, src in zip(self.states, states):
+            dst.copy_(self._to_device(src))
+
+    def current_U(self):
+        return self.Ua if self._cur == 0 else self.Ub
+
+    def other_U(self):
+        return self.Ub if self._cur == 0 else self.Ua
+
+    def U(self):
+        """Current transmembrane potential (device tensor, array shape)."""
+        return self.current_U()
+
+    # ---- stepping --------------------------------------------------------------------
+    def step(self, nsteps=1, stream=None):
+        """nsteps fused steps, one kernel launch each, on the current stream."""
+        a, b = self.current_U(), self.other_U()
+        L.check(L.lib().pdx_fd_step(self._plan, L.ptr(a), L.ptr(b), self._states_arr, L.ptr(self.DIFF),
+                                    int(nsteps), L.stream_ptr(stream)))
+        if nsteps & 1:
+            self._cur ^= 1
+        self.nsteps_done += nsteps
+
+    def step_range(self, xb, xe, stream=None):
+        """Advance only array planes [xb, xe) from current_U into other_U (no buffer swap)."""
+        L.check(L.lib().pdx_fd_step_range(self._plan, L.ptr(self.current_U()), L.ptr(self.other_U()),
+                                          self._states_arr, L.ptr(self.DIFF), int(xb), int(xe),
+                                          L.stream_ptr(stream)))
+
+    def swap(self):
+        self._cur ^= 1
+        self.nsteps_done += 1
+
+    def capture(self, nsteps):
+        """CUDA graph of ``nsteps`` steps (nsteps even keeps the buffer parity)."""
+        if nsteps % 2:
+            raise ValueError('captured blocks use an even number of steps (ping-pong parity)')
+        key = (nsteps, self._cur)
+        if key not in self._graphs:
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                a, b = self.current_U(), self.other_U()
+                with torch.cuda.graph(g, stream=s):
+                    L.check(L.lib().pdx_fd_step(self._plan, L.ptr(a), L.ptr(b), self._states_arr,
+                                                L.ptr(self.DIFF), int(nsteps), L.stream_ptr(s)))
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            self._graphs[key] = g
+        return self._graphs[key]
+
+    def run(self, nsteps, block=10):
+        """Advance nsteps using graph-captured blocks of ``block`` steps plus a remainder."""
+        block = max(2, block - block % 2)
+        nblk, rem = divmod(nsteps, block)
+        if nblk:
+            g = self.capture(block)
+            for _ in range(nblk):
+                g.replay()
+            self.nsteps_done += nblk * block
+        if rem:
+            self.step(rem)
+
+    def apply_stimulus(self, mask, intensity, stream=None):
+        """U = where(mask, max(U, intensity*mask), U): Tests/FD/Fenton/fenton.py:154-156."""
+        U = self.current_U()
+        L.check(L.lib().pdx_stim_apply(L.ptr(U), L.ptr(mask), float(np.float32(intensity)), U.numel(),
+                                       L.stream_ptr(stream)))
+
+    def launches(self):
+        return int(L.lib().pdx_fd_plan_launches(self._plan))
+
+
+class DistributedFDStepper:
+    """Slab-decomposed 3-D stepping: one process per GPU, NCCL halo exchange.
+
+    Per step: (1) the two slab-boundary planes are advanced first, (2) their exchange with
+    the neighbours runs on a side stream while (3) the interior planes are advanced on the
+    main stream; the next step starts when both are done.
+    """
+
+    def __init__(self, global_shape, spacing, dt, diff=1.0, rank=0, world=1, group=None, overlap=True, **kw):
+        self.part = SlabPartition(global_shape[0], rank, world)
+        self.group = group
+        self.overlap = overlap and world > 1
+        self.fd = FDStepper(global_shape, spacing, dt, diff, part=self.part, **kw)
+        self.comm_stream = torch.cuda.Stream(device=self.fd.device) if world > 1 else None
+        self._ev = torch.cuda.Event()
+
+    def set_global(self, U, states=None, DIFF=None):
+        """Install this rank's slab of global NumPy fields (ghost planes included)."""
+        self.fd.set_U(self.part.scatter(U))
+        if states is not None:
+            self.fd.set_states([self.part.scatter(s) for s in states])
+        if DIFF is not None:
+            self.fd.DIFF.copy_(self.fd._to_device(self.part.scatter(DIFF)))
+
+    def exchange(self, U):
+        return exchange_halos(U, self.part, self.group)
+
+    def step(self, nsteps=1):
+        fd, p = self.fd, self.part
+        for _ in range(nsteps):
+            if p.world == 1:
+                fd.step(1)
+                continue
+            out = fd.other_U()
+            main = torch.cuda.current_stream(fd.device)
+            if self.overlap and p.nloc >= 3:
+                fd.step_range(p.x_begin, p.x_begin + 1)
+                fd.step_range(p.x_end - 1, p.x_end)
+                self._ev.record(main)
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(self._ev)
+                    self.exchange(out)
+                fd.step_range(p.x_begin + 1, p.x_end - 1)
+                main.wait_stream(self.comm_stream)
+            else:
+                fd.step_range(p.x_begin, p.x_end)
+                self.exchange(out)
+            fd.swap()
+
+    def owned_U(self):
+        return self.part.owned(self.fd.current_U())

@@ -1,0 +1,280 @@
+"""GPU parity tests of the fused FD step (through the C ABI) against the NumPy oracle.
+
+Tolerances (north star: fp32, rel-L2 of the transmembrane potential <= 1e-5 after N steps,
+activation times within one dt):
+  EXACT arithmetic: rel-L2 <= 1e-6 (expected ~0: same ops in the same order)
+  FAST  arithmetic: rel-L2 <= 1e-5
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import plane_wave_ic, random_fields, rel_l2, smooth_fields
+from oracle import fd as ofd
+from oracle import ionic as oionic
+from oracle import stimulus as ostim
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'exact': 1e-6, 'fast': 1e-5}
+NSTATES = {'fenton4v': 3, 'mms2v': 1, 'ms2v': 1, None: 0}
+
+
+def make_oracle(model, dt, states):
+    if model is None:
+        return None
+    m = oionic.MODELS[model]()
+    m._dt = dt
+    for attr, s in zip(oionic.STATE_ATTRS[model], states):
+        setattr(m, attr, s.copy())
+    m._initialized = True
+    return m
+
+
+def run_gpu(shape, spacing, dt, diff, model, lap, math, kernel, U, states, nsteps, DIFF=None, use_run=False):
+    from pdensorflow_b200.fd import FDStepper
+    st = FDStepper(shape, spacing, dt, diff, model=model, lap=lap, DIFF=DIFF, math=math, kernel=kernel)
+    st.set_U(U)
+    if states:
+        st.set_states(states)
+    if use_run:
+        st.run(nsteps)
+    else:
+        st.step(nsteps)
+    torch.cuda.synchronize()
+    return st, st.U().cpu().numpy().reshape(shape), [s.cpu().numpy().reshape(shape) for s in st.states]
+
+
+def run_oracle(shape, spacing, dt, diff, model, U, states, nsteps, DIFF=None, conv=False):
+    m = make_oracle(model, dt, states)
+    Uo = ofd.fd_run(m, U.copy(), nsteps, dt, diff, spacing, DIFF=DIFF, conv=conv)
+    so = [getattr(m, a) for a in oionic.STATE_ATTRS[model]] if model else []
+    return Uo, so
+
+
+CASES_3D = [
+    # shape,          kernel
+    ((24, 20, 16), 'tma'),        # single z tile, partial y tiles
+    ((10, 19, 132), 'tma'),       # two z tiles (second one partial), odd ny
+    ((9, 11, 13), 'generic'),     # nz % 4 != 0 -> generic only
+    ((12, 16, 20), 'generic'),
+]
+
+
+@pytest.mark.parametrize('shape,kernel', CASES_3D)
+@pytest.mark.parametrize('model', ['fenton4v', 'mms2v', 'ms2v', None])
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_one_step_random_fields(cuda, shape, kernel, model, math):
+    """One step from seeded random fields: exercises every branch of the models and every
+    boundary case of the stencil (faces, edges, corners)."""
+    U, states = random_fields(shape, seed=3, nstates=NSTATES[model])
+    dt, diff, spacing = 0.1, 0.8, (1.0, 0.9, 1.1)
+    _, Ug, sg = run_gpu(shape, spacing, dt, diff, model, 'homog', math, kernel, U, states, 1)
+    Uo, so = run_oracle(shape, spacing, dt, diff, model, U, states, 1)
+    assert rel_l2(Ug, Uo) <= TOL[math]
+    for a, b in zip(sg, so):
+        assert rel_l2(a, b) <= TOL[math]
+    if math == 'exact' and model is None:
+        assert np.array_equal(Ug, Uo)          # pure stencil: bit exact
+
+
+@pytest.mark.parametrize('shape,kernel', [((24, 20, 16), 'tma'), ((9, 11, 13), 'generic')])
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_exact_mode_is_bitwise_on_most_nodes(cuda, shape, kernel, math):
+    U, states = random_fields(shape, seed=5)
+    _, Ug, sg = run_gpu(shape, (1.0, 1.0, 1.0), 0.1, 0.8, 'fenton4v', 'homog', math, kernel, U, states, 1)
+    Uo, so = run_oracle(shape, (1.0, 1.0, 1.0), 0.1, 0.8, 'fenton4v', U, states, 1)
+    frac = np.mean(Ug == Uo)
+    if math == 'exact':
+        assert frac > 0.999, frac     # only a correctly-rounded-tanh tie can differ
+        for a, b in zip(sg[:2], so[:2]):
+            assert np.array_equal(a, b)   # V and W involve no transcendental
+    assert np.max(np.abs(Ug - Uo)) < 1e-3
+
+
+@pytest.mark.parametrize('kernel,shape', [('tma', (24, 20, 16)), ('generic', (9, 11, 13))])
+@pytest.mark.parametrize('model', ['fenton4v', 'mms2v', None])
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_heterogeneous_operator(cuda, kernel, shape, model, math):
+    U, states = random_fields(shape, seed=7, nstates=NSTATES[model])
+    rng = np.random.default_rng(11)
+    DIFF = rng.uniform(0.0, 1.0, size=shape).astype(np.float32)
+    DIFF[rng.uniform(size=shape) < 0.2] = 0.0                 # holes: DIFF = 0 outside the tissue
+    dt, spacing = 0.1, (1.0, 1.0, 1.0)
+    _, Ug, sg = run_gpu(shape, spacing, dt, 1.0, model, 'heterog', math, kernel, U, states, 1, DIFF=DIFF)
+    Uo, so = run_oracle(shape, spacing, dt, 1.0, model, U, states, 1, DIFF=DIFF)
+    assert rel_l2(Ug, Uo) <= TOL[math]
+    if math == 'exact' and model is None:
+        assert np.array_equal(Ug, Uo)
+
+
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_conv_alias(cuda, math):
+    shape = (12, 16, 20)
+    U, states = random_fields(shape, seed=9)
+    spacing = (0.5, 2.0, 0.5)
+    from pdensorflow_b200.fd import FDStepper
+    st = FDStepper(shape, spacing, 0.05, 0.8, model='fenton4v', lap='conv', math=math)
+    st.set_U(U); st.set_states(states); st.step(1)
+    Ug = st.U().cpu().numpy()
+    Uo, _ = run_oracle(shape, spacing, 0.05, 0.8, 'fenton4v', U, states, 1, conv=True)
+    assert rel_l2(Ug, Uo) <= (1e-6 if math == 'exact' else 1e-5)
+
+
+@pytest.mark.parametrize('shape,kernel', [((32, 24), 'tma'), ((40, 136), 'tma'), ((17, 23), 'generic')])
+@pytest.mark.parametrize('model', ['fenton4v', 'mms2v', None])
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_2d(cuda, shape, kernel, model, math):
+    """Config 2 is the 3-D solve() pattern transcribed to 2-D."""
+    U, states = random_fields(shape, seed=13, nstates=NSTATES[model])
+    dt, diff, spacing = 0.1, 0.8, (1.0, 1.2)
+    _, Ug, sg = run_gpu(shape, spacing, dt, diff, model, 'homog', math, kernel, U, states, 1)
+    Uo, so = run_oracle(shape, spacing, dt, diff, model, U, states, 1)
+    assert rel_l2(Ug, Uo) <= TOL[math]
+    rng = np.random.default_rng(17)
+    DIFF = rng.uniform(0.0, 1.0, size=shape).astype(np.float32)
+    _, Ug, _ = run_gpu(shape, spacing, dt, 1.0, model, 'heterog', math, kernel, U, states, 1, DIFF=DIFF)
+    Uo, _ = run_oracle(shape, spacing, dt, 1.0, model, U, states, 1, DIFF=DIFF)
+    assert rel_l2(Ug, Uo) <= TOL[math]
+
+
+@pytest.mark.parametrize('nsteps', [10, 100])
+@pytest.mark.parametrize('kernel,shape', [('tma', (96, 80, 72)), ('generic', (31, 30, 29))])
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_multi_step_plane_wave(cuda, nsteps, kernel, shape, math):
+    """N steps of the examples' S1 plane-wave protocol on a non-cubic grid."""
+    U = plane_wave_ic(shape)
+    dt, diff, spacing = 0.1, 0.8, (1.0, 1.0, 1.0)
+    _, Ug, sg = run_gpu(shape, spacing, dt, diff, 'fenton4v', 'homog', math, kernel, U, [], nsteps)
+    Uo, so = run_oracle(shape, spacing, dt, diff, 'fenton4v', U,
+                        [np.ones(shape, np.float32), np.ones(shape, np.float32), np.zeros(shape, np.float32)], nsteps)
+    assert rel_l2(Ug, Uo) <= TOL[math], (nsteps, rel_l2(Ug, Uo))
+    for a, b in zip(sg, so):
+        assert rel_l2(a, b) <= 10 * TOL[math]
+
+
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_multi_step_smooth_3d_fields(cuda, math):
+    """100 steps from a smooth fully 3-D field (fronts in every direction), graph replay."""
+    shape = (48, 40, 36)
+    U, states = smooth_fields(shape, seed=21)
+    dt, diff, spacing = 0.1, 0.8, (1.0, 1.0, 1.0)
+    _, Ug, sg = run_gpu(shape, spacing, dt, diff, 'fenton4v', 'homog', math, 'tma', U, states, 100, use_run=True)
+    Uo, so = run_oracle(shape, spacing, dt, diff, 'fenton4v', U, states, 100)
+    assert rel_l2(Ug, Uo) <= TOL[math], rel_l2(Ug, Uo)
+
+
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_1000_steps_s1s2_activation_times(cuda, math):
+    """1000 steps of the S1-S2 protocol (S2 fired at step 300 on a genuine boolean mask) on 40x36x32:
+    rel-L2 and activation times (first upward crossing of -30 mV) within one dt."""
+    from pdensorflow_b200.fd import FDStepper
+    shape = (40, 36, 32)
+    dt, diff, spacing, thr = 0.1, 0.8, (1.0, 1.0, 1.0), -30.0
+    U = plane_wave_ic(shape)
+    mask = np.zeros(shape, dtype=np.float32)
+    mask[:shape[0] // 2, :shape[1] // 2, :] = 1.0
+    s2 = ostim.Stimulus({'tstart': 30.0, 'nstim': 1, 'period': 800, 'duration': dt, 'intensity': 60.0})
+    s2.set_stimregion(mask)
+    m = make_oracle('fenton4v', dt, [np.ones(shape, np.float32), np.ones(shape, np.float32),
+                                     np.zeros(shape, np.float32)])
+    Uo, act_o = ofd.fd_run(m, U.copy(), 1000, dt, diff, spacing, s2=s2, act_threshold=thr)
+
+    st = FDStepper(shape, spacing, dt, diff, model='fenton4v', math=math)
+    st.set_U(U)
+    mask_d = torch.from_numpy(mask).cuda()
+    act_g = torch.full(shape, -1, dtype=torch.int32, device='cuda')
+    prev = st.U().clone()
+    for i in range(1000):
+        st.step(1)
+        if i == 300:
+            st.apply_stimulus(mask_d, 60.0)
+        cur = st.U()
+        crossed = (prev < thr) & (cur >= thr) & (act_g < 0)
+        act_g[crossed] = i
+        prev = cur.clone()
+    Ug = st.U().cpu().numpy()
+    act_g = act_g.cpu().numpy()
+    assert rel_l2(Ug, Uo) <= TOL[math], rel_l2(Ug, Uo)
+    assert np.array_equal(act_g >= 0, act_o >= 0)
+    assert np.max(np.abs(act_g - act_o)) <= 1
+
+
+def test_shipped_quirk_all_ones_mask(cuda):
+    """F6: as shipped the S2 mask is all ones, so U = max(U, 60) on the whole grid (32^3, the
+    shipped size), 40 steps around the stimulus."""
+    from pdensorflow_b200.fd import FDStepper
+    shape = (32, 32, 32)
+    dt, diff, spacing = 0.1, 0.8, (1.0, 1.0, 1.0)
+    U = plane_wave_ic(shape)
+    s2_init = np.full(shape, -80.0, dtype=np.float32)
+    s2_init[:16, :16, :] = 20.0
+    s2 = ostim.Stimulus({'tstart': 2.0, 'nstim': 1, 'period': 800, 'duration': dt, 'intensity': 60.0})
+    s2.set_stimregion(s2_init)
+    m = make_oracle('fenton4v', dt, [np.ones(shape, np.float32), np.ones(shape, np.float32),
+                                     np.zeros(shape, np.float32)])
+    Uo = ofd.fd_run(m, U.copy(), 40, dt, diff, spacing, s2=s2)
+    st = FDStepper(shape, spacing, dt, diff, model='fenton4v', math='exact')
+    st.set_U(U)
+    mask_d = torch.from_numpy(s2.get_stimregion()).cuda()
+    for i in range(40):
+        st.step(1)
+        if i == 20:
+            st.apply_stimulus(mask_d, 60.0)
+    assert rel_l2(st.U().cpu().numpy(), Uo) <= 1e-6
+    assert Uo.min() > -81.0
+
+
+def test_tma_and_generic_kernels_agree(cuda):
+    shape = (20, 24, 260)          # three z tiles
+    U, states = random_fields(shape, seed=23)
+    out = {}
+    for kernel in ('tma', 'generic'):
+        _, Ug, sg = run_gpu(shape, (1.0, 1.0, 1.0), 0.1, 0.8, 'fenton4v', 'homog', 'exact', kernel, U, states, 3)
+        out[kernel] = (Ug, sg)
+    assert np.array_equal(out['tma'][0], out['generic'][0])
+    for a, b in zip(out['tma'][1], out['generic'][1]):
+        assert np.array_equal(a, b)
+
+
+def test_x_chunking_is_invisible(cuda):
+    """The TMA kernel marches x in chunks with 2 halo planes: results must not depend on the chunk."""
+    from pdensorflow_b200.fd import FDStepper
+    shape = (37, 16, 16)
+    U, states = random_fields(shape, seed=29)
+    res = []
+    for chunk in (0, 1, 2, 5, 37):
+        st = FDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8, model='fenton4v', math='exact', kernel='tma', x_chunk=chunk)
+        st.set_U(U); st.set_states(states); st.step(2)
+        res.append(st.U().cpu().numpy())
+    for r in res[1:]:
+        assert np.array_equal(r, res[0])
+
+
+def test_full_size_plane_wave_property(cuda):
+    """Config-3 size (512^3): a plane wave along x is independent of (y,z), so every column of the
+    512^3 GPU run must equal the oracle run on a 512x4x4 grid (size-independent property)."""
+    from pdensorflow_b200.fd import FDStepper
+    n = 512
+    free, _ = torch.cuda.mem_get_info()
+    if free < 6 * n ** 3 * 4:
+        pytest.skip('not enough device memory for 512^3')
+    nsteps = 60
+    small = (n, 4, 4)
+    Uo, _ = run_oracle(small, (1.0, 1.0, 1.0), 0.1, 0.8, 'fenton4v', plane_wave_ic(small),
+                       [np.ones(small, np.float32), np.ones(small, np.float32), np.zeros(small, np.float32)], nsteps)
+    for math in ('exact', 'fast'):
+        st = FDStepper((n, n, n), (1.0, 1.0, 1.0), 0.1, 0.8, model='fenton4v', math=math)
+        U = st.U()
+        U.fill_(-80.0)
+        U[0:2] = 20.0
+        st.run(nsteps)
+        Ug = st.U()
+        assert bool((Ug == Ug[:, :1, :1]).all())          # still planar
+        col = Ug[:, n // 3, n // 5].cpu().numpy()
+        assert rel_l2(col, Uo[:, 0, 0]) <= TOL[math]
+        # a checksum over the whole field agrees with the column (planarity + parity)
+        tot = float(Ug.double().sum())
+        assert abs(tot - float(col.astype(np.float64).sum()) * n * n) <= 1e-9 * abs(tot) + 1e-3
+        del st, U, Ug
+        torch.cuda.empty_cache()
