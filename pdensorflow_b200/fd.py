@@ -154,6 +154,8 @@ class FDStepper:
         self._states_arr = L.ptr_array(self.states)
         self._graphs = {}
         self.nsteps_done = 0
+        self._captured_launches = 0
+        self.graph_kernel_launches = 0   # kernels executed through CUDA-graph replays
 
     def __del__(self):
         try:
@@ -226,6 +228,7 @@ class FDStepper:
                                                 L.ptr(self.DIFF), int(nsteps), L.stream_ptr(s)))
             torch.cuda.current_stream(self.device).wait_stream(s)
             self._graphs[key] = g
+            self._captured_launches += nsteps
         return self._graphs[key]
 
     def run(self, nsteps, block=10):
@@ -237,6 +240,7 @@ class FDStepper:
             for _ in range(nblk):
                 g.replay()
             self.nsteps_done += nblk * block
+            self.graph_kernel_launches += nblk * block     # one kernel node per captured step
         if rem:
             self.step(rem)
 
@@ -247,7 +251,9 @@ class FDStepper:
                                        L.stream_ptr(stream)))
 
     def launches(self):
-        return int(L.lib().pdx_fd_plan_launches(self._plan))
+        """Kernel launches issued for this stepper: direct ones plus graph-replayed nodes
+        (launches recorded while capturing a graph execute only when the graph is replayed)."""
+        return int(L.lib().pdx_fd_plan_launches(self._plan)) - self._captured_launches + self.graph_kernel_launches
 
 
 class DistributedFDStepper:
