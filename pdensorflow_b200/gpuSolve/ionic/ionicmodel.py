@@ -29,6 +29,7 @@ class IonicModel:
         self._dt = dt
         self._n_nodes = n_nodes
         self._initialized = False
+        self._pb_cache = None
 
     def initialize_state_variables(self, U):
         """Create the state tensors matching U's shape (idempotent, fenton4v.py:84-91)."""
@@ -62,6 +63,7 @@ class IonicModel:
     def set_parameter(self, pname, pvalue):
         """If ``pname`` exists, set it to ``pvalue`` (scalar or per-node array)."""
         internal_name = '_{}'.format(pname)
+        self._pb_cache = None
         if internal_name in self.__dict__.keys():
             if np.ndim(pvalue) == 0 or np.size(pvalue) == 1:
                 setattr(self, internal_name, torch.tensor(float(np.float32(np.asarray(pvalue).reshape(-1)[0])),
@@ -79,6 +81,8 @@ class IonicModel:
 
     def _param_block(self, n):
         """(c_float[PDX_MAX_PARAMS], per-node pointer array or None, keep-alive list)."""
+        if self._pb_cache is not None and self._pb_cache[0] == n:
+            return self._pb_cache[1]
         params = (C.c_float * L.MAX_PARAMS)()
         parr = None
         keep = []
@@ -96,6 +100,7 @@ class IonicModel:
                 parr[i] = t.data_ptr()
             else:
                 params[i] = float(v)
+        self._pb_cache = (n, (params, parr, keep))
         return params, parr, keep
 
     def param_list(self):
