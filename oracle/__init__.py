@@ -14,24 +14,31 @@ the reference source writes them).  Every function cites the reference
 
 Pinning status (see DESIGN.md "Oracle")
 ---------------------------------------
-TensorFlow cannot be imported in this image, so the reference's own kernels
-cannot be run here.  What IS pinned:
+TensorFlow cannot be imported in this image, so the reference's TF *kernels* cannot be run
+here.  The reference's own *source* can: ``tests/golden/make_ref_golden.py`` imports the
+unmodified reference from /root/reference over ``tests/golden/tf_facade.py`` (every tf op ->
+the NumPy op with the same IEEE fp32 semantics) and freezes its outputs on seeded inputs in
+``tests/golden/ref_*.npz``.  ``tests/test_ref_golden_cpu.py`` holds this oracle to those
+fixtures:
 
-* FEM local/global assembly - checked against the reference's own pure-NumPy
-  code (``gpuSolve/matrices/localMass.py``, ``localStiffness.py`` and the
-  TF-free half of ``globalMatrices.py``), imported by file path in this
-  container; golden vectors under ``tests/golden/`` with the generating script.
-* Ionic models - the reference's unit-test properties (rest fixed point,
-  determinism, |dU| bound: ``Tests/CICD/unit/test_ionic.py:66-97``).
-* 1-D mass/stiffness closed forms (``test_matrices.py:117-160``), csr_axpby
-  (``test_csr_axpby.py:62-96``), PCG gold-solution recovery
-  (``test_conjgrad.py:117-162``), 1-D/2-D mMS conduction velocity +-10 %
-  (``test_mms_1d.py:140-176``, ``nightly/test_mms_2d_regression.py``).
-* Stimulus timing - the step windows worked out in SURVEY.md section 8a row S.
+* bit-exact: all six diffop Laplacians (2-D/3-D homogeneous, conv, heterogeneous,
+  anisotropic), ``enforce_boundary``, Stimulus step/float-time windows, one ``differentiate``
+  call of all five ionic models (per-node parameters included), paced single-cell
+  trajectories of all five models (three TTP cell types) through an action potential, the
+  ``Tests/FD/Fenton/fenton.py`` example run end to end (homogeneous, conv and heterogeneous
+  operators, the all-ones S2 quirk included);
+* CRN/TTP lookup tables: samples within 2e-6 relative (NumPy's fp32 exp is SIMD-dispatch
+  dependent) and fp64 column checksums;
+* ``MonodomainSolver.step`` (assembly + RCM + stimulus + Jacobi-PCG) on 1-D and 2-D meshes:
+  identical CG iteration counts every step, potentials within 1e-6 relative L2;
+* FEM local/global assembly also against the reference's pure-NumPy code imported by file
+  path (``tests/golden/fem_golden.npz``, ``make_fem_golden.py``), plus the reference's unit-test
+  properties (rest fixed point, closed-form 1-D matrices, csr_axpby, CG gold recovery, CV +-10 %).
 
-PARITY UNPINNED by any reference golden vector: the FD Laplacians,
-``enforce_boundary`` and Fenton-4v trajectories away from rest (the reference
-holds no test or fixture for them).  For those the restatement below is the
-only arbiter; it is frozen into ``tests/golden/*.npz`` with seeds.
+What the facade cannot pin: ulp-level differences between TF's Eigen/XLA transcendental
+kernels (tanh, exp, log) and the correctly rounded fp32 values used here, and TF's
+unspecified reduction order in ``reduce_sum``; both are far inside the north-star tolerance
+(rel-L2 <= 1e-5).  Only the explicit mass-lumped FEM step has no reference
+implementation at all and is therefore PARITY UNPINNED.
 """
-from . import fd, ionic, stimulus  # noqa: F401
+from . import fd, ionic, ionic_lut, stimulus  # noqa: F401

@@ -91,6 +91,59 @@ def laplace_heterog_3d(X0, DIFF0, DX, DY, DZ):
     return ((e - w) / dxsq + (n - s) / dysq + (u - d) / dzsq).astype(np.float32)
 
 
+def laplace_heterog_aniso_3d(X0, DIFF0, AVEC0, DX, DY, DZ):
+    """gpuSolve/diffop3D/laplace_heterogeneous_anisotropic_diffusion.py:3-95.
+
+    DIFF0[...,0] = sigma_t, DIFF0[...,1] = sigma_l - sigma_t; AVEC0[...,0:6] = the fibre dyadic
+    (a1a1, a1a2, a1a3, a2a2, a2a3, a3a3).  C = sigma_t*I + (sigma_l - sigma_t) a(x)a on the
+    symmetric-padded arrays (:40-45).  For each axis ``a`` and side ``sg`` the face flux is
+        sg*0.5*( sum over b = x,y,z of T_b ),
+        T_a = (C_aa[sg e_a] + C_aa[0]) * (X[sg e_a] - X[0]) / D_a                       (normal part)
+        T_b = 0.5*(C_ab[sg e_a + e_b] + C_ab[sg e_a - e_b]) * (X[sg e_a + e_b] - X[sg e_a - e_b]) / D_b
+    (:50-90; centred transverse differences taken AT the neighbour cell), and
+        lap = (e - w)/DX + (n - s)/DY + (u - d)/DZ                                      (:93).
+    Note the result is divided by the spacing once here and once inside each flux.
+    """
+    X = _sympad(X0)
+    pad4 = ((1, 1), (1, 1), (1, 1), (0, 0))
+    D = np.pad(DIFF0, pad4, mode='symmetric')
+    A = np.pad(AVEC0, pad4, mode='symmetric')
+    st, dl = D[..., 0], D[..., 1]
+    # symmetric tensor components indexed by the (unordered) axis pair
+    C = {(0, 0): st + A[..., 0] * dl, (0, 1): A[..., 1] * dl, (0, 2): A[..., 2] * dl,
+         (1, 1): st + A[..., 3] * dl, (1, 2): A[..., 4] * dl, (2, 2): st + A[..., 5] * dl}
+    h = (F(DX), F(DY), F(DZ))
+    n = X0.shape
+    half = F(0.5)
+
+    def at(arr, off):
+        return arr[1 + off[0]:1 + off[0] + n[0], 1 + off[1]:1 + off[1] + n[1], 1 + off[2]:1 + off[2] + n[2]]
+
+    def e(axis, s=1):
+        v = [0, 0, 0]
+        v[axis] = s
+        return np.array(v)
+
+    zero = np.zeros(3, dtype=int)
+    flux = {}
+    for a in range(3):
+        for sg in (1, -1):
+            total = None
+            for b in range(3):
+                if b == a:
+                    Caa = C[(a, a)]
+                    t = (at(Caa, sg * e(a)) + at(Caa, zero)) * (at(X, sg * e(a)) - at(X, zero)) / h[a]
+                else:
+                    Cab = C[(min(a, b), max(a, b))]
+                    p_, m_ = sg * e(a) + e(b), sg * e(a) - e(b)
+                    t = half * (at(Cab, p_) + at(Cab, m_)) * (at(X, p_) - at(X, m_)) / h[b]
+                total = t if total is None else total + t
+            flux[(a, sg)] = (half if sg > 0 else F(-0.5)) * total
+    lap = ((flux[(0, 1)] - flux[(0, -1)]) / h[0] + (flux[(1, 1)] - flux[(1, -1)]) / h[1]
+           + (flux[(2, 1)] - flux[(2, -1)]) / h[2])
+    return lap.astype(np.float32)
+
+
 def laplace_homog_2d(X0, DX, DY):
     """gpuSolve/diffop2D/laplace_homogeneous_isotropic_diffusion.py:3-36."""
     X = _sympad(X0)
