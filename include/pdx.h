@@ -32,12 +32,14 @@
 extern "C" {
 #endif
 
-#define PDX_VERSION 100
+#define PDX_VERSION 110
 
-/* ionic models: gpuSolve/ionic/{fenton4v,mms2v,ms2v}.py */
-enum { PDX_MODEL_NONE = 0, PDX_MODEL_FENTON4V = 1, PDX_MODEL_MMS2V = 2, PDX_MODEL_MS2V = 3 };
+/* ionic models: gpuSolve/ionic/{fenton4v,mms2v,ms2v,courtemanche_ramirez_nattel,
+ * ten_tusscher_panfilov}.py.  CRN and TTP are the lookup-table models (pdx_lut_model below). */
+enum { PDX_MODEL_NONE = 0, PDX_MODEL_FENTON4V = 1, PDX_MODEL_MMS2V = 2, PDX_MODEL_MS2V = 3,
+       PDX_MODEL_CRN = 4, PDX_MODEL_TTP = 5 };
 /* diffusion operators: gpuSolve/diffop3D/__init__.py:25-28, diffop2D/__init__.py:20-21 */
-enum { PDX_LAP_HOMOG = 0, PDX_LAP_CONV = 1, PDX_LAP_HETEROG = 2 };
+enum { PDX_LAP_HOMOG = 0, PDX_LAP_CONV = 1, PDX_LAP_HETEROG = 2, PDX_LAP_ANISO = 3 };
 /* arithmetic: EXACT = op-for-op fp32 in the reference's evaluation order, IEEE division,
  * no FMA contraction, correctly rounded tanh.  FAST = same formulas with reciprocal
  * multiplies, FMA contraction and ex2/rcp-based tanh (|err| ~1e-7); meets the
@@ -47,7 +49,9 @@ enum { PDX_MATH_EXACT = 0, PDX_MATH_FAST = 1 };
 enum { PDX_KERNEL_AUTO = 0, PDX_KERNEL_GENERIC = 1, PDX_KERNEL_TMA = 2 };
 
 #define PDX_MAX_PARAMS 24
-#define PDX_MAX_STATES 4
+#define PDX_MAX_STATES 4          /* closed-form models (FENTON4V / MMS2V / MS2V) */
+#define PDX_LUT_MAX_STATES 24     /* lookup-table models: CRN 19, TTP 22 state arrays */
+#define PDX_LUT_MAX_CONSTS 64
 
 /* Parameter vector layouts (fp32, the reference's defaults are returned by
  * pdx_model_default_params):
@@ -57,6 +61,9 @@ enum { PDX_KERNEL_AUTO = 0, PDX_KERNEL_GENERIC = 1, PDX_KERNEL_TMA = 2 };
  *  MS2V  (ms2v.py:46-53):   tau_in tau_out tau_open tau_close u_gate  -     vmin DV (8)
  *  (DV is the models' _DV attribute = vmax - vmin formed in fp32 at construction.)
  * State arrays: FENTON4V V,W,S (init 1,1,0); MMS2V/MS2V H (init 1). */
+/* For CRN / TTP pdx_model_num_params returns the length of pdx_lut_model.consts and
+ * pdx_model_num_states 19 / 22; pdx_model_default_params does not apply (the constants are
+ * folded from the model's Python attributes by the host, as the reference folds them). */
 int pdx_model_num_params(int model);
 int pdx_model_num_states(int model);
 int pdx_model_default_params(int model, float* out /* PDX_MAX_PARAMS */);
@@ -94,6 +101,54 @@ typedef struct pdx_fd_desc {
 
 typedef struct pdx_fd_plan pdx_fd_plan;
 
+/* ---- lookup-table ionic models (CourtemancheRamirezNattel, TenTusscherPanfilov) ------------
+ * The reference builds three uniform tables per model on the host in NumPy at the model's dt
+ * (construct_tables: courtemanche_ramirez_nattel.py:255-391, ten_tusscher_panfilov.py:234-371)
+ * and reads them by linear interpolation (_interpolate, :241-252 / :220-231).  The host shim
+ * does the same and hands the tables (device, row-major, `stride` floats per row) plus the
+ * scalar constants (Python-scalar sub-expressions folded in float64, then rounded to fp32 - TF's
+ * rule) to the kernels.  Layouts (columns / constants / state order):
+ *  CRN tab[0] V   [-200,200) res 0.1, 32 cols: (A,B) pairs m h j oa oi ua ui xr xs d f w, then GKur
+ *                 INaK IbNa GCaL*(V-65) NaCa_a NaCa_b V*GbCa GNa*(V-ENa)
+ *      tab[1] Cai [3e-4,30) res 3e-4, 5 cols: Iup_ca buf IpCa_ca conCa fCa_A
+ *      tab[2] fn  [-2e-11,1e-10) res 2e-15, 3 cols: u_A v_A v_B
+ *      consts: RT/F Ko kACh Gto factorGKur GKr GKs GK1 factorGtr tau_tr factorGrel k_rel
+ *              maxIup/maxCaup C_dCa_rel KmCsqn F*Voli C_dCaup C_B1d C_B1e C_Fn1 C_Fn2 B_fCa B_u  (23)
+ *      states: Ca_rel Ca_up Cai Ki d f f_Ca h j m oa oi u ua ui v w xr xs             (19)
+ *  TTP tab[0] V   [-800,800) res 0.05, 27 cols: (A,B) pairs D F2 F H J M R S Xr1 Xr2 Xs, then a2
+ *                 NaCa_A NaCa_B rec_iNaK rec_ipK
+ *      tab[1] CaSS [1e-5,10) res 1e-5, 2 cols: FCaSS_A FCaSS_B
+ *      tab[2] V-Ek [-800,800) res 0.05, 1 col: rec_iK1
+ *      consts: RTONF 0.5*RTONF Cao Ko Ko+pKNa*Nao pKNa Nao GpCa KpCa Fconst F_RT 0.5*F_RT sqrt(Ko/5.4)
+ *              GNa pmf_INaK KmNa GbCa GbNa GpK GK1 Vleak Vmaxup Kup^2 Vxfer invVcF*Cm maxsr maxsr-minsr EC
+ *              1/(2VcF) Cm Vsr/Vc Bufc*Kbufc Kbufc k4 k2 k1 k3 Vrel Bufsr*Kbufsr Kbufsr Vc/Vss Vsr/Vss
+ *              1/(2VssF) Bufss*Kbufss Kbufss                                            (45)
+ *      states: GCaL GKr GKs Gto CaSR CaSS Cai F F2 FCaSS H J Ki M Nai R R_bar S Xr1 Xr2 Xs D   (22)
+ * Arithmetic is always op-for-op fp32 in the reference's order (math_mode is ignored). */
+typedef struct pdx_lut_table {
+    const float* data;       /* device, nrows x stride */
+    int32_t nrows, ncols, stride;
+    float   mn, mx, res, step;   /* f32(mn), f32(mx), f32(res), f32(1.0/res) */
+    int32_t mx_idx;              /* int((mx-mn)*step) - 1 (float64, as the reference computes it) */
+} pdx_lut_table;
+
+typedef struct pdx_lut_model {
+    int32_t model;               /* PDX_MODEL_CRN / PDX_MODEL_TTP */
+    int32_t nconsts;
+    float   dt;                  /* f32(dt) of the forward-Euler concentration updates */
+    pdx_lut_table tab[3];
+    float   consts[PDX_LUT_MAX_CONSTS];
+} pdx_lut_model;
+
+/* IonicModel.differentiate for CRN / TTP (courtemanche_ramirez_nattel.py:423-514,
+ * ten_tusscher_panfilov.py:405-523): writes dU (may be NULL), advances the states in place;
+ * if rhs0_out != NULL also writes U + dt*(dU + I0) (monodomainSolver.py:100-103). */
+int pdx_ionic_lut_step(const pdx_lut_model* m, int64_t n, const float* U, float* const* states,
+                       float* dU_out, const float* I0, float* rhs0_out, void* stream);
+/* attach the tables/constants to a plan whose descriptor names PDX_MODEL_CRN / PDX_MODEL_TTP
+ * (required before pdx_fd_step; states[] then holds 19 / 22 arrays) */
+int pdx_fd_plan_set_lut(pdx_fd_plan* p, const pdx_lut_model* m);
+
 void pdx_fd_desc_init(pdx_fd_desc* d);                      /* zero + defaults */
 int  pdx_fd_plan_create(const pdx_fd_desc* d, pdx_fd_plan** out);
 void pdx_fd_plan_destroy(pdx_fd_plan* p);
@@ -105,9 +160,12 @@ int64_t pdx_fd_plan_launches(const pdx_fd_plan* p);
 /* nsteps fused steps, ping-ponging between U_a and U_b: step k reads (k even ? U_a : U_b)
  * and writes the other; the result is in U_b when nsteps is odd, in U_a when even.
  * states[]: the model's state arrays, updated in place.  DIFF: diffusivity field for
- * PDX_LAP_HETEROG (else NULL).  All arrays have the descriptor's [nx][ny][nz] shape. */
+ * PDX_LAP_HETEROG (else NULL).  All arrays have the descriptor's [nx][ny][nz] shape.
+ * PDX_LAP_ANISO: DIFF is [nx][ny][nz][2] (sigma_t, sigma_l - sigma_t) and the fibre dyadic
+ * [nx][ny][nz][6] is attached with pdx_fd_plan_set_avec. */
 int pdx_fd_step(pdx_fd_plan* p, float* U_a, float* U_b, float* const* states,
                 const float* DIFF, int nsteps, void* stream);
+int pdx_fd_plan_set_avec(pdx_fd_plan* p, const float* AVEC);
 /* one step restricted to planes [xb, xe) (boundary-first / interior split used to
  * overlap the halo exchange); same clamps as the plan. */
 int pdx_fd_step_range(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states,
@@ -122,6 +180,9 @@ int pdx_fd_step_range(pdx_fd_plan* p, const float* U_in, float* U_out, float* co
 int pdx_fd_laplace(int ndim, int nx, int ny, int nz, float dx, float dy, float dz,
                    int lap_kind, int math_mode, const float* X0, const float* DIFF,
                    float* out, void* stream);
+/* laplace_heterogeneous_anisotropic_diffusion.py:3-95: DIFF0 [nx][ny][nz][2], AVEC0 [nx][ny][nz][6] */
+int pdx_fd_laplace_aniso(int nx, int ny, int nz, float dx, float dy, float dz, const float* X0,
+                         const float* DIFF0, const float* AVEC0, float* out, void* stream);
 /* enforce_boundary: Tests/FD/Fenton/fenton.py:46-53 (dirichlet=0) /
  * LaplaceSolver/laplaceSolver.py:44-52 (dirichlet=1) */
 int pdx_fd_enforce_boundary(int ndim, int nx, int ny, int nz, int dirichlet, float value,

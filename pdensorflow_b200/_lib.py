@@ -9,11 +9,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libpdx.so')
 
-MODEL_NONE, MODEL_FENTON4V, MODEL_MMS2V, MODEL_MS2V = 0, 1, 2, 3
-LAP_HOMOG, LAP_CONV, LAP_HETEROG = 0, 1, 2
+MODEL_NONE, MODEL_FENTON4V, MODEL_MMS2V, MODEL_MS2V, MODEL_CRN, MODEL_TTP = 0, 1, 2, 3, 4, 5
+LAP_HOMOG, LAP_CONV, LAP_HETEROG, LAP_ANISO = 0, 1, 2, 3
 MATH_EXACT, MATH_FAST = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TMA = 0, 1, 2
 MAX_PARAMS, MAX_STATES = 24, 4
+LUT_MAX_STATES, LUT_MAX_CONSTS = 24, 64
 
 
 class PdxError(RuntimeError):
@@ -32,6 +33,18 @@ class FdDesc(C.Structure):
         ('x_chunk', C.c_int32),
         ('params', C.c_float * MAX_PARAMS),
     ]
+
+
+class LutTable(C.Structure):
+    """struct pdx_lut_table (include/pdx.h)."""
+    _fields_ = [('data', C.c_void_p), ('nrows', C.c_int32), ('ncols', C.c_int32), ('stride', C.c_int32),
+                ('mn', C.c_float), ('mx', C.c_float), ('res', C.c_float), ('step', C.c_float), ('mx_idx', C.c_int32)]
+
+
+class LutModel(C.Structure):
+    """struct pdx_lut_model (include/pdx.h)."""
+    _fields_ = [('model', C.c_int32), ('nconsts', C.c_int32), ('dt', C.c_float), ('tab', LutTable * 3),
+                ('consts', C.c_float * LUT_MAX_CONSTS)]
 
 
 _lib = None
@@ -56,6 +69,10 @@ _SIGNATURES = {
     'pdx_fd_enforce_boundary': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
     'pdx_ionic_step': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(_P), C.c_int64, _P,
                                  C.POINTER(_P), _P, C.c_float, _P, _P, _P]),
+    'pdx_ionic_lut_step': (C.c_int, [C.POINTER(LutModel), C.c_int64, _P, C.POINTER(_P), _P, _P, _P, _P]),
+    'pdx_fd_plan_set_lut': (C.c_int, [_P, C.POINTER(LutModel)]),
+    'pdx_fd_plan_set_avec': (C.c_int, [_P, _P]),
+    'pdx_fd_laplace_aniso': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     'pdx_stim_apply': (C.c_int, [_P, _P, C.c_float, C.c_int64, _P]),
     'pdx_csr_spmv': (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P]),
     'pdx_pcg_create': (C.c_int, [C.c_int32, _P, _P, _P, _P, C.POINTER(_P)]),
@@ -93,7 +110,10 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def ptr_array(tensors, n=MAX_STATES):
+def ptr_array(tensors, n=None):
+    tensors = list(tensors)
+    if n is None:
+        n = MAX_STATES if len(tensors) <= MAX_STATES else LUT_MAX_STATES
     arr = (C.c_void_p * n)()
     for i, t in enumerate(tensors):
         arr[i] = None if t is None else t.data_ptr()

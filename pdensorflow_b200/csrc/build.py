@@ -16,7 +16,9 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 BUILD = os.path.join(HERE, 'build')
 LIB = os.path.join(PKG, 'libpdx.so')
-SOURCES = ['pdx_api.cu', 'pdx_fd_generic.cu', 'pdx_fd_tma.cu', 'pdx_fem.cu']
+SOURCES = ['pdx_api.cu', 'pdx_fd_generic.cu', 'pdx_fd_tma.cu', 'pdx_fem.cu', 'pdx_ionic_lut.cu']
+# per-source flags: the lookup-table models are evaluated op-for-op (no FMA contraction)
+EXTRA = {'pdx_ionic_lut.cu': ['-fmad=false']}
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr']
@@ -50,7 +52,7 @@ def build(force=False, verbose=False):
         src = os.path.join(HERE, s)
         obj = os.path.join(BUILD, s.replace('.cu', '.o'))
         if force or _stale(src, obj):
-            cmd = [nvcc] + ARCH + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            cmd = [nvcc] + ARCH + FLAGS + EXTRA.get(s, []) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
             jobs.append((s, cmd))
 
     def run(job):

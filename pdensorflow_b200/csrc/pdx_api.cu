@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <unordered_map>
 #include "pdx_internal.h"
 
@@ -87,6 +88,9 @@ struct pdx_fd_plan {
     pdx_fd_desc d;
     int kernel;
     FdArgs base;
+    LutArgs lut;
+    bool has_lut;
+    const float* avec;
     int box_y, box_z;
     std::unordered_map<const void*, CUtensorMap> maps;
     int64_t launches;
@@ -116,6 +120,8 @@ int pdx_model_num_params(int model) {
         case PDX_MODEL_FENTON4V: return FK_NPARAM;
         case PDX_MODEL_MMS2V:
         case PDX_MODEL_MS2V: return MS_NPARAM;
+        case PDX_MODEL_CRN:
+        case PDX_MODEL_TTP: return lut_model_num_consts(model);
     }
     return -1;
 }
@@ -125,13 +131,45 @@ int pdx_model_num_states(int model) {
         case PDX_MODEL_FENTON4V: return 3;
         case PDX_MODEL_MMS2V:
         case PDX_MODEL_MS2V: return 1;
+        case PDX_MODEL_CRN: return 19;
+        case PDX_MODEL_TTP: return 22;
     }
     return -1;
+}
+
+static bool is_lut_model(int model) { return model == PDX_MODEL_CRN || model == PDX_MODEL_TTP; }
+
+static int fill_lut_args(const pdx_lut_model* m, LutArgs* L) {
+    if (!m || !is_lut_model(m->model)) { set_error("pdx_lut_model: model must be PDX_MODEL_CRN or PDX_MODEL_TTP"); return 1; }
+    if (m->nconsts != lut_model_num_consts(m->model)) { set_error("pdx_lut_model: wrong number of constants"); return 1; }
+    static const int min_cols[2][3] = {{32, 5, 3}, {27, 2, 1}};
+    std::memset(L, 0, sizeof(*L));
+    for (int t = 0; t < 3; ++t) {
+        const pdx_lut_table& T = m->tab[t];
+        const int need = min_cols[m->model == PDX_MODEL_TTP][t];
+        if (!T.data || T.ncols < need || T.stride < T.ncols || T.nrows < 2 || T.mx_idx < 1 || T.mx_idx > T.nrows - 1 ||
+            !(T.res > 0.0f)) {
+            set_error("pdx_lut_model: bad table descriptor");
+            return 1;
+        }
+        if (((uintptr_t)T.data % 8) != 0 || (T.stride % 2 != 0 && T.stride != 1)) {
+            set_error("pdx_lut_model: tables must be 8-byte aligned with an even row stride");
+            return 1;
+        }
+        L->tab[t] = LutTab{T.data, T.stride, T.mn, T.mx, T.res, T.step, T.mx_idx};
+    }
+    for (int i = 0; i < m->nconsts; ++i) L->c[i] = m->consts[i];
+    L->dt = m->dt;
+    return 0;
 }
 int pdx_model_default_params(int model, float* out) {
     const int np = pdx_model_num_params(model);
     if (np < 0 || !out) { set_error("pdx_model_default_params: bad arguments"); return 1; }
     for (int i = 0; i < PDX_MAX_PARAMS; ++i) out[i] = 0.0f;
+    if (model == PDX_MODEL_CRN || model == PDX_MODEL_TTP) {
+        set_error("pdx_model_default_params: lookup-table models take pdx_lut_model constants");
+        return 1;
+    }
     const float* src = model == PDX_MODEL_FENTON4V ? kFkDefaults : model == PDX_MODEL_MMS2V ? kMmsDefaults : kMsDefaults;
     for (int i = 0; i < np; ++i) out[i] = src[i];
     return 0;
@@ -160,6 +198,7 @@ static int fill_args(const pdx_fd_desc& d, FdArgs* a) {
     a->zclo = 1; a->zchi = d.nz - 2;
     a->dirichlet = d.dirichlet; a->dirichlet_value = d.dirichlet_value;
     a->dt = d.dt; a->coef = d.coef;
+    a->hx = d.dx; a->hy = d.dy; a->hz = d.dz;
     a->hxsq = d.dx * d.dx; a->hysq = d.dy * d.dy; a->hzsq = d.dz * d.dz;
     a->rhxsq = (float)(1.0 / (double)a->hxsq);
     a->rhysq = (float)(1.0 / (double)a->hysq);
@@ -169,7 +208,7 @@ static int fill_args(const pdx_fd_desc& d, FdArgs* a) {
     const float ix = 1.0f / a->hxsq, iy = 1.0f / a->hysq, iz = 1.0f / a->hzsq;
     a->kx = iz; a->ky = iy; a->kz = ix;
     a->kc = -2.0f * ((ix + iy) + iz);
-    fill_model_params(d.model, d.params, d.dt, &a->mp);
+    if (!is_lut_model(d.model)) fill_model_params(d.model, d.params, d.dt, &a->mp);
     return 0;
 }
 
@@ -183,8 +222,11 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
         return 1;
     }
     if (pdx_model_num_states(d.model) < 0) { set_error("pdx_fd_plan_create: unknown model"); return 1; }
-    if (d.lap_kind < PDX_LAP_HOMOG || d.lap_kind > PDX_LAP_HETEROG) { set_error("pdx_fd_plan_create: unknown lap_kind"); return 1; }
-    if (d.lap_kind == PDX_LAP_CONV && d.ndim == 2) { set_error("pdx_fd_plan_create: the conv operator is 3-D only"); return 1; }
+    if (d.lap_kind < PDX_LAP_HOMOG || d.lap_kind > PDX_LAP_ANISO) { set_error("pdx_fd_plan_create: unknown lap_kind"); return 1; }
+    if ((d.lap_kind == PDX_LAP_CONV || d.lap_kind == PDX_LAP_ANISO) && d.ndim == 2) {
+        set_error("pdx_fd_plan_create: the conv and anisotropic operators are 3-D only");
+        return 1;
+    }
     if (d.math_mode != PDX_MATH_EXACT && d.math_mode != PDX_MATH_FAST) { set_error("pdx_fd_plan_create: unknown math_mode"); return 1; }
     if (d.ndim == 2) {
         d.x_begin = 0; d.x_end = 1; d.x_clamp_lo = 0; d.x_clamp_hi = 0;
@@ -197,7 +239,7 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
         return 1;
     }
     int kernel = d.kernel;
-    const bool tma_ok = fd_tma_supported(d);
+    const bool tma_ok = fd_tma_supported(d) && !is_lut_model(d.model) && d.lap_kind != PDX_LAP_ANISO;
     if (kernel == PDX_KERNEL_AUTO) kernel = tma_ok ? PDX_KERNEL_TMA : PDX_KERNEL_GENERIC;
     if (kernel == PDX_KERNEL_TMA && !tma_ok) {
         set_error("pdx_fd_plan_create: TMA kernel needs nz % 4 == 0, no Dirichlet, no EXACT conv");
@@ -208,6 +250,8 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     p->d = d;
     p->kernel = kernel;
     p->launches = 0;
+    p->has_lut = false;
+    p->avec = nullptr;
     fill_args(d, &p->base);
     int ty, tz;
     fd_tma_tile_geometry(d, &ty, &tz, &p->box_y, &p->box_z);
@@ -230,6 +274,20 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
 }
 
 void pdx_fd_plan_destroy(pdx_fd_plan* p) { delete p; }
+
+int pdx_fd_plan_set_lut(pdx_fd_plan* p, const pdx_lut_model* m) {
+    if (!p || !m) { set_error("pdx_fd_plan_set_lut: null argument"); return 1; }
+    if (m->model != p->d.model) { set_error("pdx_fd_plan_set_lut: model differs from the plan's descriptor"); return 1; }
+    if (fill_lut_args(m, &p->lut)) return 1;
+    p->has_lut = true;
+    return 0;
+}
+
+int pdx_fd_plan_set_avec(pdx_fd_plan* p, const float* AVEC) {
+    if (!p || !AVEC) { set_error("pdx_fd_plan_set_avec: null argument"); return 1; }
+    p->avec = AVEC;
+    return 0;
+}
 int pdx_fd_plan_kernel(const pdx_fd_plan* p) { return p ? p->kernel : -1; }
 int64_t pdx_fd_plan_launches(const pdx_fd_plan* p) { return p ? p->launches : -1; }
 
@@ -239,15 +297,26 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
     if (!Uin || !Uout || Uin == Uout) { set_error("pdx_fd_step: U_in/U_out must be distinct non-null buffers"); return 1; }
     const int ns = pdx_model_num_states(d.model);
     if (ns > 0 && !states) { set_error("pdx_fd_step: states required"); return 1; }
-    if (d.lap_kind == PDX_LAP_HETEROG && !DIFF) { set_error("pdx_fd_step: DIFF required for the heterogeneous operator"); return 1; }
+    if ((d.lap_kind == PDX_LAP_HETEROG || d.lap_kind == PDX_LAP_ANISO) && !DIFF) {
+        set_error("pdx_fd_step: DIFF required for the heterogeneous / anisotropic operator");
+        return 1;
+    }
+    if (d.lap_kind == PDX_LAP_ANISO && !p->avec) { set_error("pdx_fd_step: call pdx_fd_plan_set_avec first"); return 1; }
     FdArgs a = p->base;
-    a.Uin = Uin; a.Uout = Uout; a.DIFF = DIFF;
+    a.Uin = Uin; a.Uout = Uout; a.DIFF = DIFF; a.AVEC = p->avec;
+    const bool lut = is_lut_model(d.model);
+    if (lut && !p->has_lut) { set_error("pdx_fd_step: call pdx_fd_plan_set_lut first"); return 1; }
     for (int i = 0; i < ns; ++i) {
         if (!states[i]) { set_error("pdx_fd_step: null state array"); return 1; }
-        a.st[i] = states[i];
+        if (lut) p->lut.st[i] = states[i]; else a.st[i] = states[i];
     }
     a.xb = xb; a.xe = xe;
     if (xe <= xb) return 0;
+    if (lut) {
+        const int rc = launch_fd_lut(d, a, p->lut, s);
+        if (!rc) p->launches += 1;
+        return rc;
+    }
     int kernel = p->kernel;
     if (kernel == PDX_KERNEL_TMA) {
         bool aligned = ((uintptr_t)Uin % 16 == 0) && ((uintptr_t)Uout % 16 == 0) &&
@@ -265,7 +334,14 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
         if (get_map(p, Uin, &mU)) return 1;
         if (d.lap_kind == PDX_LAP_HETEROG) { if (get_map(p, DIFF, &mD)) return 1; } else mD = mU;
         pdx_fd_desc dd = d;
-        if (dd.lap_kind == PDX_LAP_CONV) dd.lap_kind = PDX_LAP_HOMOG;   // FAST conv alias
+        if (dd.lap_kind == PDX_LAP_CONV) {
+            // FAST conv alias of the 7-point kernel.  The reference's conv kernel puts 1/dz^2 on
+            // the axis-0 taps and 1/dx^2 on the axis-2 taps (laplace_convolution...py:31-39), so the
+            // alias swaps the two spacings to reproduce it for DX != DZ.
+            dd.lap_kind = PDX_LAP_HOMOG;
+            std::swap(a.hxsq, a.hzsq);
+            std::swap(a.rhxsq, a.rhzsq);
+        }
         rc = launch_fd_tma(dd, a, *mU, *mD, s);
     } else {
         rc = launch_fd_generic(d, a, s);
@@ -301,6 +377,7 @@ int pdx_fd_laplace(int ndim, int nx, int ny, int nz, float dx, float dy, float d
     }
     if (lap_kind == PDX_LAP_HETEROG && !DIFF) { set_error("pdx_fd_laplace: DIFF required"); return 1; }
     if (lap_kind == PDX_LAP_CONV && ndim == 2) { set_error("pdx_fd_laplace: the conv operator is 3-D only"); return 1; }
+    if (lap_kind < PDX_LAP_HOMOG || lap_kind > PDX_LAP_HETEROG) { set_error("pdx_fd_laplace: unknown lap_kind (use pdx_fd_laplace_aniso)"); return 1; }
     pdx_fd_desc d;
     pdx_fd_desc_init(&d);
     d.ndim = ndim; d.nx = nx; d.ny = ny; d.nz = nz; d.dx = dx; d.dy = dy; d.dz = dz;
@@ -312,6 +389,36 @@ int pdx_fd_laplace(int ndim, int nx, int ny, int nz, float dx, float dy, float d
     a.dxlo = 0; a.dxhi = nx - 1;
     a.Uin = X0; a.Uout = out; a.DIFF = DIFF;
     return launch_fd_laplace_only(lap_kind, math_mode, a, (cudaStream_t)stream);
+}
+
+int pdx_fd_laplace_aniso(int nx, int ny, int nz, float dx, float dy, float dz, const float* X0, const float* DIFF0,
+                         const float* AVEC0, float* out, void* stream) {
+    if (!X0 || !DIFF0 || !AVEC0 || !out || nx < 1 || ny < 1 || nz < 1) { set_error("pdx_fd_laplace_aniso: bad arguments"); return 1; }
+    pdx_fd_desc d;
+    pdx_fd_desc_init(&d);
+    d.ndim = 3; d.nx = nx; d.ny = ny; d.nz = nz; d.dx = dx; d.dy = dy; d.dz = dz;
+    d.lap_kind = PDX_LAP_ANISO; d.math_mode = PDX_MATH_EXACT; d.model = PDX_MODEL_NONE;
+    d.x_begin = 0; d.x_end = nx; d.x_clamp_lo = 0; d.x_clamp_hi = nx - 1;
+    FdArgs a;
+    fill_args(d, &a);
+    a.yclo = 0; a.ychi = ny - 1; a.zclo = 0; a.zchi = nz - 1;   // pure symmetric pad, no enforce_boundary
+    a.dxlo = 0; a.dxhi = nx - 1;
+    a.Uin = X0; a.Uout = out; a.DIFF = DIFF0; a.AVEC = AVEC0;
+    return launch_fd_laplace_aniso(a, (cudaStream_t)stream);
+}
+
+int pdx_ionic_lut_step(const pdx_lut_model* m, int64_t n, const float* U, float* const* states, float* dU_out,
+                       const float* I0, float* rhs0_out, void* stream) {
+    if (!m || !U || !states || n < 0) { set_error("pdx_ionic_lut_step: bad arguments"); return 1; }
+    if (n == 0) return 0;
+    LutArgs L;
+    if (fill_lut_args(m, &L)) return 1;
+    const int ns = pdx_model_num_states(m->model);
+    for (int i = 0; i < ns; ++i) {
+        if (!states[i]) { set_error("pdx_ionic_lut_step: null state array"); return 1; }
+        L.st[i] = states[i];
+    }
+    return launch_lut_ionic(m->model, L, n, U, dU_out, I0, rhs0_out, (cudaStream_t)stream);
 }
 
 int pdx_fd_enforce_boundary(int ndim, int nx, int ny, int nz, int dirichlet, float value, const float* X, float* out,

@@ -3,32 +3,11 @@
 // loads (L1/L2 provide the reuse).  This is the fallback for shapes the TMA tile kernel
 // does not take (nz % 4 != 0, conv alias, Dirichlet) and the independent implementation
 // the TMA kernel is cross-checked against.
-#include "pdx_internal.h"
+#include "pdx_stencil.cuh"
 
 namespace pdx {
 
 namespace {
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-
-struct Field {
-    const float* U;
-    int ny, nz;
-    int xclo, xchi, yclo, ychi, zclo, zchi;
-    int dirichlet;
-    float dval;
-    // value of U0 = enforce_boundary(U) at an in-array index
-    __device__ __forceinline__ float at(int i, int j, int k) const {
-        if (dirichlet) {
-            const bool inside = i >= xclo && i <= xchi && j >= yclo && j <= ychi && k >= zclo && k <= zchi;
-            return inside ? U[((size_t)i * ny + j) * nz + k] : dval;
-        }
-        i = clampi(i, xclo, xchi);
-        j = clampi(j, yclo, ychi);
-        k = clampi(k, zclo, zchi);
-        return U[((size_t)i * ny + j) * nz + k];
-    }
-};
 
 // MODE: 0 = fused step (writes U1, advances states), 1 = Laplacian only (writes lap)
 template <int MODEL, int LAP, int MATH, int MODE>
@@ -39,41 +18,9 @@ __global__ void __launch_bounds__(256) fd_generic_kernel(const __grid_constant__
     if (k >= a.nz || j >= a.ny || i >= a.xe) return;
     const size_t idx = ((size_t)i * a.ny + j) * a.nz + k;
 
-    Field f{a.Uin, a.ny, a.nz, a.xclo, a.xchi, a.yclo, a.ychi, a.zclo, a.zchi, a.dirichlet, a.dirichlet_value};
-    // symmetric pad: neighbour indices are first clamped to the (global) array bounds
-    const int im = max(i - 1, a.dxlo), ip = min(i + 1, a.dxhi);
-    const int jm = max(j - 1, 0), jp = min(j + 1, a.ny - 1);
-    const int km = max(k - 1, 0), kp = min(k + 1, a.nz - 1);
-
-    const float c = f.at(i, j, k);
-    float lap;
-    if (LAP == PDX_LAP_HETEROG) {
-        const float* D = a.DIFF;
-        auto dat = [&](int ii, int jj, int kk) { return D[((size_t)ii * a.ny + jj) * a.nz + kk]; };
-        const float dc = dat(i, j, k);
-        lap = lap_axis_het<MATH>(f.at(i, jm, k), c, f.at(i, jp, k), dat(i, jm, k), dc, dat(i, jp, k), a.hysq, a.rhysq);
-        if (a.has_x) {
-            const float lx = lap_axis_het<MATH>(f.at(im, j, k), c, f.at(ip, j, k), dat(im, j, k), dc, dat(ip, j, k),
-                                                a.hxsq, a.rhxsq);
-            lap = madd<MATH>(lx, lap);
-        }
-        lap = madd<MATH>(lap, lap_axis_het<MATH>(f.at(i, j, km), c, f.at(i, j, kp), dat(i, j, km), dc, dat(i, j, kp),
-                                                 a.hzsq, a.rhzsq));
-    } else if (LAP == PDX_LAP_CONV) {
-        // 3x3x3 VALID convolution, taps summed in kernel memory order
-        float o = mmul<MATH>(a.kx, f.at(im, j, k));
-        o = madd<MATH>(o, mmul<MATH>(a.ky, f.at(i, jm, k)));
-        o = madd<MATH>(o, mmul<MATH>(a.kz, f.at(i, j, km)));
-        o = madd<MATH>(o, mmul<MATH>(a.kc, c));
-        o = madd<MATH>(o, mmul<MATH>(a.kz, f.at(i, j, kp)));
-        o = madd<MATH>(o, mmul<MATH>(a.ky, f.at(i, jp, k)));
-        o = madd<MATH>(o, mmul<MATH>(a.kx, f.at(ip, j, k)));
-        lap = o;
-    } else {
-        lap = lap_axis<MATH>(f.at(i, jm, k), c, f.at(i, jp, k), a.hysq, a.rhysq);
-        if (a.has_x) lap = madd<MATH>(lap_axis<MATH>(f.at(im, j, k), c, f.at(ip, j, k), a.hxsq, a.rhxsq), lap);
-        lap = madd<MATH>(lap, lap_axis<MATH>(f.at(i, j, km), c, f.at(i, j, kp), a.hzsq, a.rhzsq));
-    }
+    const Field f = make_field(a);
+    float c;
+    const float lap = node_laplacian<LAP, MATH>(a, f, i, j, k, c);
     if (MODE == 1) {
         a.Uout[idx] = lap;
         return;
@@ -114,6 +61,7 @@ int launch_lap(int lap, int math, const FdArgs& a, cudaStream_t s) {
         case PDX_LAP_HOMOG:   return launch_math<MODEL, PDX_LAP_HOMOG, MODE>(math, a, s);
         case PDX_LAP_CONV:    return launch_math<MODEL, PDX_LAP_CONV, MODE>(math, a, s);
         case PDX_LAP_HETEROG: return launch_math<MODEL, PDX_LAP_HETEROG, MODE>(math, a, s);
+        case PDX_LAP_ANISO:   return launch_one<MODEL, PDX_LAP_ANISO, PDX_MATH_EXACT, MODE>(a, s);
     }
     set_error("unknown lap_kind");
     return 1;
@@ -136,13 +84,17 @@ int launch_fd_laplace_only(int lap_kind, int math_mode, const FdArgs& a, cudaStr
     return launch_lap<PDX_MODEL_NONE, 1>(lap_kind, math_mode, a, s);
 }
 
+int launch_fd_laplace_aniso(const FdArgs& a, cudaStream_t s) {
+    return launch_one<PDX_MODEL_NONE, PDX_LAP_ANISO, PDX_MATH_EXACT, 1>(a, s);
+}
+
 // ---------------------------------------------------------------- enforce_boundary
 __global__ void __launch_bounds__(256) enforce_boundary_kernel(const __grid_constant__ FdArgs a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int i = blockIdx.z;
     if (k >= a.nz || j >= a.ny) return;
-    Field f{a.Uin, a.ny, a.nz, a.xclo, a.xchi, a.yclo, a.ychi, a.zclo, a.zchi, a.dirichlet, a.dirichlet_value};
+    const Field f = make_field(a);
     a.Uout[((size_t)i * a.ny + j) * a.nz + k] = f.at(i, j, k);
 }
 

@@ -15,6 +15,7 @@ struct FdArgs {
     float*       Uout;
     float*       st[PDX_MAX_STATES];
     const float* DIFF;
+    const float* AVEC;           // fibre dyadic [nx][ny][nz][6] (ANISO)
     int nx, ny, nz;
     int xb, xe;                  // planes advanced
     int xclo, xchi;              // clamp of stencil plane indices for U (enforce_boundary + pad)
@@ -26,10 +27,25 @@ struct FdArgs {
     int dirichlet;
     float dirichlet_value;
     float dt, coef;
+    float hx, hy, hz;            // spacings (ANISO divides by them)
     float hxsq, hysq, hzsq;      // dx*dx ... (fp32 products)
     float rhxsq, rhysq, rhzsq;   // reciprocals (FAST)
     float kx, ky, kz, kc;        // conv-kernel taps (CONV): see laplace_convolution...py:30-40
     ModelParams mp;
+};
+
+// lookup-table models (pdx_ionic_lut.cu)
+struct LutTab {
+    const float* t;
+    int stride;
+    float mn, mx, res, step;
+    int mx_idx;
+};
+struct LutArgs {
+    LutTab tab[3];
+    float  c[PDX_LUT_MAX_CONSTS];
+    float* st[PDX_LUT_MAX_STATES];
+    float  dt;
 };
 
 void set_error(const std::string& msg);
@@ -45,6 +61,11 @@ int launch_enforce_boundary(const FdArgs& a, cudaStream_t s);
 int launch_ionic(int model, int math, const float* params, const float* const* parr, int64_t n, const float* U,
                  float* const* states, float* dU, float dt, const float* I0, float* rhs0, cudaStream_t s);
 int launch_stim(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s);
+int launch_fd_laplace_aniso(const FdArgs& a, cudaStream_t s);
+int lut_model_num_consts(int model);
+int launch_lut_ionic(int model, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0, float* rhs0,
+                     cudaStream_t s);
+int launch_fd_lut(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s);
 // TMA-staged tile kernel: requires nz % 4 == 0, 16-byte aligned arrays, HOMOG/HETEROG
 bool fd_tma_supported(const pdx_fd_desc& d);
 int  launch_fd_tma(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mapU, const CUtensorMap& mapD,

@@ -20,7 +20,7 @@ from . import _lib as L
 
 _MODEL_IDS = {None: L.MODEL_NONE, 'none': L.MODEL_NONE, 'heat': L.MODEL_NONE,
               'fenton4v': L.MODEL_FENTON4V, 'mms2v': L.MODEL_MMS2V, 'ms2v': L.MODEL_MS2V}
-_LAP_IDS = {'homog': L.LAP_HOMOG, 'conv': L.LAP_CONV, 'heterog': L.LAP_HETEROG}
+_LAP_IDS = {'homog': L.LAP_HOMOG, 'conv': L.LAP_CONV, 'heterog': L.LAP_HETEROG, 'aniso': L.LAP_ANISO}
 _MATH_IDS = {'exact': L.MATH_EXACT, 'fast': L.MATH_FAST}
 _KERNEL_IDS = {'auto': L.KERNEL_AUTO, 'generic': L.KERNEL_GENERIC, 'tma': L.KERNEL_TMA}
 STATE_INIT = {L.MODEL_FENTON4V: (1.0, 1.0, 0.0), L.MODEL_MMS2V: (1.0,), L.MODEL_MS2V: (1.0,), L.MODEL_NONE: ()}
@@ -93,12 +93,16 @@ class FDStepper:
     spacing:  (DX, DY, DZ) or (DX, DY)
     dt, diff: Python floats as in the examples' config (fenton.py:170-183); the
               coefficient f32(diff*dt) is formed in float64 first, like the reference does
-    model:    'fenton4v' | 'mms2v' | 'ms2v' | None (heat equation)
-    lap:      'homog' | 'conv' | 'heterog' (then DIFF is required and carries the diffusivity)
+    model:    'fenton4v' | 'mms2v' | 'ms2v' | None (heat equation), or an IonicModel instance of
+              pdensorflow_b200.gpuSolve.ionic - required for the lookup-table models
+              (CourtemancheRamirezNattel, TenTusscherPanfilov), whose tables/constants/state
+              arrays the instance owns
+    lap:      'homog' | 'conv' | 'heterog' (DIFF [W,H,D] carries the diffusivity) |
+              'aniso' (DIFF [W,H,D,2] and AVEC [W,H,D,6] as laplace_heterog_aniso takes them)
     """
 
     def __init__(self, shape, spacing, dt, diff=1.0, model='fenton4v', params=None, lap='homog', DIFF=None,
-                 math='fast', kernel='auto', part=None, device=None, x_chunk=0):
+                 math='fast', kernel='auto', part=None, device=None, x_chunk=0, AVEC=None):
         self.device = torch.device('cuda' if device is None else device)
         if self.device.type != 'cuda':
             raise L.PdxError('FDStepper needs a CUDA device: there is no CPU path')
@@ -106,7 +110,17 @@ class FDStepper:
         if self.ndim not in (2, 3) or len(spacing) != self.ndim:
             raise ValueError('shape/spacing must both be 2-D or 3-D')
         self.part = part
-        self.model_id = _MODEL_IDS[model]
+        self.ionic = None
+        if model is not None and not isinstance(model, str):
+            self.ionic = model
+            self.model_id = model._MODEL_ID
+            if params is None and self.model_id not in (L.MODEL_CRN, L.MODEL_TTP):
+                params = model.param_list()
+        else:
+            self.model_id = _MODEL_IDS[model]
+        self.is_lut = self.model_id in (L.MODEL_CRN, L.MODEL_TTP)
+        if self.is_lut and self.ionic is None:
+            raise ValueError('lookup-table models are passed as IonicModel instances')
         self.lap_id = _LAP_IDS[lap]
         d = L.FdDesc()
         L.lib().pdx_fd_desc_init(C.byref(d))
@@ -125,11 +139,11 @@ class FDStepper:
             d.dy, d.dz = (float(np.float32(s)) for s in spacing)
         self.array_shape = (d.nx, d.ny, d.nz) if self.ndim == 3 else (d.ny, d.nz)
         d.dt = float(np.float32(dt))
-        d.coef = float(np.float32(dt)) if lap == 'heterog' else float(np.float32(float(diff) * float(dt)))
+        d.coef = float(np.float32(dt)) if lap in ('heterog', 'aniso') else float(np.float32(float(diff) * float(dt)))
         d.lap_kind, d.model = self.lap_id, self.model_id
         d.math_mode, d.kernel = _MATH_IDS[math], _KERNEL_IDS[kernel]
         d.x_chunk = int(x_chunk)
-        if self.model_id != L.MODEL_NONE:
+        if self.model_id != L.MODEL_NONE and not self.is_lut:
             p = L.default_params(self.model_id) if params is None else list(params)
             for i, v in enumerate(p):
                 d.params[i] = float(v)
@@ -143,13 +157,26 @@ class FDStepper:
         # buffers
         self.Ua = torch.empty(self.array_shape, dtype=torch.float32, device=self.device)
         self.Ub = torch.empty_like(self.Ua)
-        self.states = [torch.full(self.array_shape, v, dtype=torch.float32, device=self.device)
-                       for v in STATE_INIT[self.model_id]]
-        self.DIFF = None
+        if self.is_lut:
+            # the model instance owns tables, constants and the 19/22 state arrays
+            self.ionic._dt = dt
+            self.ionic.initialize_state_variables(self.Ua)
+            self.states = self.ionic.state_tensors()
+            L.check(L.lib().pdx_fd_plan_set_lut(self._plan, C.byref(self.ionic.lut_desc())))
+        else:
+            self.states = [torch.full(self.array_shape, v, dtype=torch.float32, device=self.device)
+                           for v in STATE_INIT[self.model_id]]
+        self.DIFF = self.AVEC = None
         if lap == 'heterog':
             if DIFF is None:
                 raise ValueError("lap='heterog' needs DIFF")
             self.DIFF = self._to_device(DIFF)
+        elif lap == 'aniso':
+            if DIFF is None or AVEC is None:
+                raise ValueError("lap='aniso' needs DIFF [W,H,D,2] and AVEC [W,H,D,6]")
+            self.DIFF = self._to_device(DIFF, extra=(2,))
+            self.AVEC = self._to_device(AVEC, extra=(6,))
+            L.check(L.lib().pdx_fd_plan_set_avec(self._plan, L.ptr(self.AVEC)))
         self._cur = 0            # 0: current U is Ua
         self._states_arr = L.ptr_array(self.states)
         self._graphs = {}
@@ -166,14 +193,15 @@ class FDStepper:
             pass
 
     # ---- data in/out -----------------------------------------------------------------
-    def _to_device(self, A):
+    def _to_device(self, A, extra=()):
         if isinstance(A, torch.Tensor):
             t = A.to(device=self.device, dtype=torch.float32)
         else:
             t = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float32)).to(self.device)
-        if self.part is not None and tuple(t.shape) != tuple(self.array_shape):
+        shape = tuple(self.array_shape) + tuple(extra)
+        if self.part is not None and tuple(t.shape) != shape:
             raise ValueError('distributed steppers take local arrays (SlabPartition.scatter)')
-        return t.reshape(self.array_shape).contiguous()
+        return t.reshape(shape).contiguous()
 
     def set_U(self, U):
         self.current_U().copy_(self._to_device(U))

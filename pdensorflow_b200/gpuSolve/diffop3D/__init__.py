@@ -48,9 +48,20 @@ def laplace_heterogeneous_isotropic_diffusion(X0, DIFF0, DX, DY, DZ):
 
 
 def laplace_heterogeneous_anisotropic_diffusion(X0, DIFF0, AVEC0, DX, DY, DZ):
-    """19-point fibre-tensor operator (laplace_heterogeneous_anisotropic_diffusion.py:3-95).
-    Not built yet ("build last"): fails loudly, no fallback."""
-    raise NotImplementedError('laplace_heterog_aniso is not implemented in pdensorflow_b200 yet')
+    """19-point fibre-tensor operator (laplace_heterogeneous_anisotropic_diffusion.py:3-95):
+    DIFF0 [W,H,D,2] = (sigma_t, sigma_l - sigma_t), AVEC0 [W,H,D,6] = the fibre dyadic."""
+    X0 = L.require_cuda(B.as_tensor(X0), 'X0')
+    if X0.dim() != 3:
+        raise L.PdxError('diffop3D operators take [W,H,D] tensors')
+    D = L.require_cuda(B.as_tensor(DIFF0, like=X0), 'DIFF0')
+    A = L.require_cuda(B.as_tensor(AVEC0, like=X0), 'AVEC0')
+    if tuple(D.shape) != tuple(X0.shape) + (2,) or tuple(A.shape) != tuple(X0.shape) + (6,):
+        raise L.PdxError('DIFF0 must be [W,H,D,2] and AVEC0 [W,H,D,6]')
+    out = torch.empty_like(X0)
+    nx, ny, nz = X0.shape
+    L.check(L.lib().pdx_fd_laplace_aniso(nx, ny, nz, B.as_float(DX), B.as_float(DY), B.as_float(DZ), L.ptr(X0),
+                                         L.ptr(D), L.ptr(A), L.ptr(out), L.stream_ptr()))
+    return out
 
 
 laplace_heterog = laplace_heterogeneous_isotropic_diffusion

@@ -46,21 +46,25 @@ class _Plan:
 
 
 _PLANS = {}
-_LAPS = {'homog': L.LAP_HOMOG, 'conv': L.LAP_CONV, 'heterog': L.LAP_HETEROG}
+_LAPS = {'homog': L.LAP_HOMOG, 'conv': L.LAP_CONV, 'heterog': L.LAP_HETEROG, 'aniso': L.LAP_ANISO}
 
 
-def fused_solve(model, U, dt, diff, spacing, lap='homog', DIFF=None, math='fast', kernel='auto'):
+def fused_solve(model, U, dt, diff, spacing, lap='homog', DIFF=None, AVEC=None, math='fast', kernel='auto'):
     """One explicit step U -> U1 in a single kernel.  ``model`` is an IonicModel of this
-    package (its states advance in place by ``dt``) or None for the heat equation."""
+    package (its states advance in place by ``dt``) or None for the heat equation.
+    ``lap='heterog'``: DIFF [W,H,D] carries the diffusivity; ``lap='aniso'``: DIFF [W,H,D,2] and
+    AVEC [W,H,D,6] as laplace_heterog_aniso takes them (both used as ``U0 + dt*dU + dt*lap``)."""
     U = L.require_cuda(U, 'U')
     ndim = U.dim()
     if ndim not in (2, 3) or len(spacing) != ndim:
         raise L.PdxError('fused_solve: U must be 2-D/3-D with matching spacing')
     model_id = L.MODEL_NONE if model is None else model._MODEL_ID
-    params = () if model is None else tuple(model.param_list())
+    is_lut = model_id in (L.MODEL_CRN, L.MODEL_TTP)
+    params = () if (model is None or is_lut) else tuple(model.param_list())
     sp = tuple(B.as_float(s) for s in spacing)
-    coef = float(np.float32(dt)) if lap == 'heterog' else float(np.float32(float(diff) * float(dt)))
-    key = (tuple(U.shape), sp, float(np.float32(dt)), coef, lap, math, kernel, model_id, params, U.device.index)
+    coef = float(np.float32(dt)) if lap in ('heterog', 'aniso') else float(np.float32(float(diff) * float(dt)))
+    key = (tuple(U.shape), sp, float(np.float32(dt)), coef, lap, math, kernel, model_id, params, U.device.index,
+           id(model) if is_lut else 0)
     plan = _PLANS.get(key)
     if plan is None:
         d = L.FdDesc()
@@ -87,9 +91,16 @@ def fused_solve(model, U, dt, diff, spacing, lap='homog', DIFF=None, math='fast'
         states = model.state_tensors()
         if float(np.float32(model._dt)) != float(np.float32(dt)):
             raise L.PdxError('fused_solve: model._dt (%r) differs from dt (%r)' % (model._dt, dt))
-    D = None
-    if lap == 'heterog':
+    if is_lut:
+        L.check(L.lib().pdx_fd_plan_set_lut(plan.handle, C.byref(model.lut_desc())))
+    D = A = None
+    if lap in ('heterog', 'aniso'):
         D = L.require_cuda(B.as_tensor(DIFF, like=U), 'DIFF')
+    if lap == 'aniso':
+        A = L.require_cuda(B.as_tensor(AVEC, like=U), 'AVEC')
+        if tuple(D.shape) != tuple(U.shape) + (2,) or tuple(A.shape) != tuple(U.shape) + (6,):
+            raise L.PdxError('aniso: DIFF must be [W,H,D,2] and AVEC [W,H,D,6]')
+        L.check(L.lib().pdx_fd_plan_set_avec(plan.handle, L.ptr(A)))
     U1 = torch.empty_like(U)
     L.check(L.lib().pdx_fd_step(plan.handle, L.ptr(U), L.ptr(U1), L.ptr_array(states), L.ptr(D), 1,
                                 L.stream_ptr()))

@@ -37,12 +37,14 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_host_only_entry_points(lib):
     h = lib.lib()
-    assert h.pdx_version() == 100
+    assert h.pdx_version() >= 110
     assert h.pdx_model_num_states(lib.MODEL_FENTON4V) == 3 and h.pdx_model_num_states(lib.MODEL_MMS2V) == 1
     assert h.pdx_model_num_params(lib.MODEL_FENTON4V) == 23 and h.pdx_model_num_states(99) == -1
     p = lib.default_params(lib.MODEL_FENTON4V)
     assert abs(p[0] - 3.33) < 1e-6 and p[21] == -80.0 and p[22] == 100.0
     assert lib.default_params(lib.MODEL_MS2V)[0] == pytest.approx(0.3)
+    assert h.pdx_model_num_states(lib.MODEL_CRN) == 19 and h.pdx_model_num_states(lib.MODEL_TTP) == 22
+    assert h.pdx_model_num_params(lib.MODEL_CRN) == 23 and h.pdx_model_num_params(lib.MODEL_TTP) == 45
 
 
 def test_argument_validation_fails_loudly(lib):

@@ -291,3 +291,37 @@ def test_monodomain_solver_vs_reference_source(tag, ionic, etype, stim):
     assert list(mo.niters) == list(g[tag + '_iters'])
     err = np.linalg.norm(np.stack(frames).astype(np.float64) - ref) / np.linalg.norm(ref.astype(np.float64))
     assert err < 1e-6, err
+
+
+# ------------------------------------------------------------------------------ product host code
+PROD_CRN_V = ['m_A', 'm_B', 'h_A', 'h_B', 'j_A', 'j_B', 'oa_A', 'oa_B', 'oi_A', 'oi_B', 'ua_A', 'ua_B', 'ui_A', 'ui_B',
+              'xr_A', 'xr_B', 'xs_A', 'xs_B', 'd_A', 'd_B', 'f_A', 'f_B', 'w_A', 'w_B', 'GKur', 'INaK', 'IbNa', 'ICaL_v',
+              'NaCa_a', 'NaCa_b', 'IbCa_v', 'INa_v']
+PROD_TTP_V = ['D_A', 'D_B', 'F2_A', 'F2_B', 'F_A', 'F_B', 'H_A', 'H_B', 'J_A', 'J_B', 'M_A', 'M_B', 'R_A', 'R_B', 'S_A',
+              'S_B', 'Xr1_A', 'Xr1_B', 'Xr2_A', 'Xr2_B', 'Xs_A', 'Xs_B', 'a2', 'NaCa_A', 'NaCa_B', 'rec_iNaK', 'rec_ipK']
+
+
+class _HostTab:
+    def __init__(self, ht, names):
+        self.table, self.names = ht.array[:, :ht.ncols], names
+
+
+def test_product_table_builder_matches_reference_construct_tables():
+    """The host-side construct_tables of the shipped CRN/TTP classes (NumPy, no GPU needed) in the
+    kernel's column layout (include/pdx.h) against the reference's tables."""
+    from pdensorflow_b200.gpuSolve.ionic.courtemanche_ramirez_nattel import CourtemancheRamirezNattel
+    from pdensorflow_b200.gpuSolve.ionic.ten_tusscher_panfilov import TenTusscherPanfilov
+    g = gold('ref_luts.npz')
+    with np.errstate(all='ignore'):
+        c = [t.finish() for t in CourtemancheRamirezNattel(dt=0.02)._build_tables()]
+        t_ = [t.finish() for t in TenTusscherPanfilov(dt=0.02)._build_tables()]
+        te = [t.finish() for t in TenTusscherPanfilov(dt=0.02, cell_type='ENDO')._build_tables()]
+    check_table(g, 'crn_V_tab', _HostTab(c[0], PROD_CRN_V), CRN_V_COLS)
+    check_table(g, 'crn_Cai_tab', _HostTab(c[1], ['Iup_ca', 'buf', 'IpCa_ca', 'conCa', 'fCa_A']), CRN_CAI_COLS)
+    check_table(g, 'crn_fn_tab', _HostTab(c[2], ['u_A', 'v_A', 'v_B']), CRN_FN_COLS)
+    check_table(g, 'ttp_V_tab_lut', _HostTab(t_[0], PROD_TTP_V), TTP_V_COLS)
+    check_table(g, 'ttp_CaSS_tab', _HostTab(t_[1], ['FCaSS_A', 'FCaSS_B']), TTP_CASS_COLS)
+    check_table(g, 'ttp_VEk_tab', _HostTab(t_[2], ['rec_iK1']), TTP_VEK_COLS)
+    check_table(g, 'ttpendo_V_tab_lut', _HostTab(te[0], PROD_TTP_V), TTP_V_COLS)
+    assert all(t.stride % 2 == 0 or t.stride == 1 for t in c + t_)
+    assert len(CourtemancheRamirezNattel(dt=0.02)._fold_constants.__code__.co_varnames) >= 1

@@ -1,0 +1,67 @@
+"""Throughput of every fused-step variant (CUDA events, graph-free), one JSON line each ->
+the table in DESIGN.md / profiles/.  Not the contract bench (bench.py is)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from pdensorflow_b200.fd import FDStepper
+from pdensorflow_b200.gpuSolve.ionic import CourtemancheRamirezNattel, TenTusscherPanfilov
+
+PEAK = 6536.4
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                             'MEASURED_PEAKS.json')))['hbm_gbs'])
+except Exception:
+    pass
+BYTES = {'fenton4v': 32, 'mms2v': 16, 'ms2v': 16, None: 8, 'crn': 8 + 19 * 8, 'ttp': 8 + 18 * 8 + 4 * 4}
+
+
+def bench(shape, model='fenton4v', math='fast', kernel='auto', lap='homog', nsteps=40, reps=3, dt=0.1, diff=0.8):
+    name = model
+    mobj = model
+    u_rest = -80.0
+    if model == 'crn':
+        mobj, u_rest, dt, diff = CourtemancheRamirezNattel(), -81.2, 0.02, 0.1
+    elif model == 'ttp':
+        mobj, u_rest, dt, diff = TenTusscherPanfilov(), -86.2, 0.02, 0.1
+    DIFF = torch.full(shape, diff, device='cuda') if lap == 'heterog' else None
+    st = FDStepper(shape, (1.0,) * len(shape), dt, diff, model=mobj, math=math, kernel=kernel, lap=lap, DIFF=DIFF)
+    U = st.U()
+    U.fill_(u_rest)
+    U[0:2] = 20.0
+    st.step(20 if name in ('crn', 'ttp') else 200)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st.step(nsteps)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / nsteps)
+    n = int(np.prod(shape))
+    nb = BYTES[name] + (4 if lap == 'heterog' else 0)
+    assert bool(torch.isfinite(st.U()).all())
+    print(json.dumps({'grid': list(shape), 'model': name or 'heat', 'lap': lap, 'math': math, 'kernel': st.kernel,
+                      'ms_per_step': round(best, 4), 'gnode_steps_per_s': round(n / best / 1e6, 2),
+                      'bytes_per_node_step': nb, 'algorithmic_gbs': round(n * nb / best / 1e6, 1),
+                      'frac_of_measured_hbm_peak': round(n * nb / best / 1e6 / PEAK, 3)}), flush=True)
+
+
+if __name__ == '__main__':
+    torch.cuda.set_device(0)
+    S = (512, 512, 512)
+    bench(S)
+    bench(S, math='exact')
+    bench(S, kernel='generic')
+    bench(S, lap='heterog')
+    bench(S, model='mms2v')
+    bench(S, model='ms2v')
+    bench(S, model=None)
+    bench((1024, 1024), nsteps=400)
+    bench((4096, 4096), nsteps=100)
+    bench((256, 256, 256), model='crn', nsteps=10)
+    bench((256, 256, 256), model='ttp', nsteps=10)
