@@ -96,8 +96,12 @@ def test_3d_operators_match_oracle_bitwise(cuda, shape):
     assert np.array_equal(laplace_homog(Xd, DX, DY, DZ).cpu().numpy(), ofd.laplace_homog_3d(X, 0.5, 1.25, 2.0))
     assert np.array_equal(laplace_heterog(Xd, Dd, DX, DY, DZ).cpu().numpy(), ofd.laplace_heterog_3d(X, D, 0.5, 1.25, 2.0))
     assert np.array_equal(laplace_conv_homog(Xd, DX, DY, DZ).cpu().numpy(), ofd.laplace_conv_homog_3d(X, 0.5, 1.25, 2.0))
-    with pytest.raises(NotImplementedError):
-        laplace_heterog_aniso(Xd, Dd, Dd, DX, DY, DZ)
+    DF = rng.uniform(0.1, 1.0, shape + (2,)).astype(np.float32)
+    AV = rng.uniform(-1.0, 1.0, shape + (6,)).astype(np.float32)
+    got = laplace_heterog_aniso(Xd, torch.from_numpy(DF).cuda(), torch.from_numpy(AV).cuda(), DX, DY, DZ)
+    assert np.array_equal(got.cpu().numpy(), ofd.laplace_heterog_aniso_3d(X, DF, AV, 0.5, 1.25, 2.0))
+    with pytest.raises(Exception):
+        laplace_heterog_aniso(Xd, Dd, Dd, DX, DY, DZ)                # wrong channel counts
     with pytest.raises(Exception):
         laplace_homog(torch.zeros(4, 4), 1.0, 1.0, 1.0)              # wrong rank
 
