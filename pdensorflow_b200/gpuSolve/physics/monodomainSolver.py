@@ -89,8 +89,23 @@ class MonodomainSolver(HeatSolver):
     def solve_step(self, U, I0):
         m = self._ionic_model
         states = m.state_tensors()
-        params, parr, keep = m._param_block(U.numel())
         dt32 = float(np.float32(self._dt))
+        if m._MODEL_ID in (L.MODEL_CRN, L.MODEL_TTP):
+            # lookup-table models: one pointwise kernel writes RHS0 = U + dt*(dU + I0)
+            if self._explicit_lumped:
+                raise L.PdxError('explicit_lumped is not available for the lookup-table ionic models')
+            if float(np.float32(m._dt)) != dt32:
+                raise L.PdxError('ionic model dt (%r) differs from the solver dt (%r)' % (m._dt, self._dt))
+            rhs0, rhs = self._work()
+            import ctypes as C
+            L.check(L.lib().pdx_ionic_lut_step(C.byref(m.lut_desc()), U.numel(), L.ptr(U),
+                                               L.ptr_array(states, L.LUT_MAX_STATES), None, L.ptr(I0), L.ptr(rhs0),
+                                               L.stream_ptr()))
+            self._MASS.matvec(rhs0, out=rhs)
+            self._Solver.set_X0(U)
+            self._Solver.solve_inplace(rhs, self._Solver.X())
+            return self._Solver.X()
+        params, parr, keep = m._param_block(U.numel())
         if self._explicit_lumped:
             if parr is not None:
                 raise L.PdxError('explicit_lumped step takes uniform ionic parameters')
