@@ -1,6 +1,7 @@
 // pdx_api.cu - the C ABI of libpdx.so (see include/pdx.h): plans, tensor maps, dispatch.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <utility>
@@ -93,8 +94,24 @@ struct pdx_fd_plan {
     const float* avec;
     int box_y, box_z;
     std::unordered_map<const void*, CUtensorMap> maps;
+    std::unordered_map<const void*, CUtensorMap> smaps;   // state arrays (box without halo)
+    bool tma_states;
     int64_t launches;
 };
+
+static int get_state_map(pdx_fd_plan* p, const float* ptr, const CUtensorMap** out) {
+    auto it = p->smaps.find(ptr);
+    if (it == p->smaps.end()) {
+        CUtensorMap m;
+        int by, bz;
+        fd_tma_state_box(&by, &bz);
+        if (make_tensor_map_3d(&m, ptr, p->d.nx, p->d.ny, p->d.nz, 1, by, bz)) return 1;
+        if (p->smaps.size() > 64) p->smaps.clear();
+        it = p->smaps.emplace(ptr, m).first;
+    }
+    *out = &it->second;
+    return 0;
+}
 
 static int get_map(pdx_fd_plan* p, const float* ptr, const CUtensorMap** out) {
     auto it = p->maps.find(ptr);
@@ -252,6 +269,10 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     p->launches = 0;
     p->has_lut = false;
     p->avec = nullptr;
+    {   // states staged by TMA unless PDX_TMA_STATES=0 (A/B switch for profiling)
+        const char* e = std::getenv("PDX_TMA_STATES");
+        p->tma_states = !(e && e[0] == '0');
+    }
     fill_args(d, &p->base);
     int ty, tz;
     fd_tma_tile_geometry(d, &ty, &tz, &p->box_y, &p->box_z);
@@ -267,7 +288,11 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
         std::memset(&dummy, 0, sizeof(dummy));
         pdx_fd_desc dd = d;
         if (dd.lap_kind == PDX_LAP_CONV) dd.lap_kind = PDX_LAP_HOMOG;
-        if (launch_fd_tma(dd, a, dummy, dummy, nullptr)) { delete p; return 1; }
+        const CUtensorMap* none[PDX_MAX_STATES] = {nullptr, nullptr, nullptr, nullptr};
+        if (launch_fd_tma(dd, a, dummy, dummy, nullptr, nullptr) || launch_fd_tma(dd, a, dummy, dummy, none, nullptr)) {
+            delete p;
+            return 1;
+        }
     }
     *out = p;
     return 0;
@@ -342,7 +367,13 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
             std::swap(a.hxsq, a.hzsq);
             std::swap(a.rhxsq, a.rhzsq);
         }
-        rc = launch_fd_tma(dd, a, *mU, *mD, s);
+        const CUtensorMap* mS[PDX_MAX_STATES] = {nullptr, nullptr, nullptr, nullptr};
+        // 2-D fields give each CTA a single plane: nothing to pipeline, the register path is faster
+        const bool use_tst = p->tma_states && ns > 0 && a.has_x;
+        if (use_tst)
+            for (int i = 0; i < ns; ++i)
+                if (get_state_map(p, states[i], &mS[i])) return 1;
+        rc = launch_fd_tma(dd, a, *mU, *mD, use_tst ? mS : nullptr, s);
     } else {
         rc = launch_fd_generic(d, a, s);
     }

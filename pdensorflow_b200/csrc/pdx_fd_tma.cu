@@ -24,17 +24,22 @@ constexpr int COLS = TZ + 2 * ZH;    // 136 floats per smem row
 constexpr int NWARP = 8;
 constexpr int NTHREADS = NWARP * 32;
 constexpr int STAGES = 6;            // ring depth (3 planes in use + 3 in flight)
+constexpr int SSTAGES = 3;           // state ring depth (TMA-staged states: planes in flight per CTA)
 
 constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-template <int R, bool HET>
+template <int R, bool HET, int NST = 0>
 struct Geo {
     static constexpr int TY = NWARP * R;
     static constexpr int ROWS = TY + 2;
     static constexpr int FIELD_BYTES = round_up(ROWS * COLS * 4, 128);
     static constexpr int SLOT_BYTES = FIELD_BYTES * (HET ? 2 : 1);
     static constexpr int TX_BYTES = ROWS * COLS * 4 * (HET ? 2 : 1);
-    static constexpr int SMEM_BYTES = STAGES * SLOT_BYTES + STAGES * 8;
+    // TMA-staged states: NST arrays, one (TY x TZ) box each per plane, SSTAGES planes deep
+    static constexpr int ST_BYTES = TY * TZ * 4;
+    static constexpr int SRING_BYTES = SSTAGES * NST * ST_BYTES;
+    static constexpr int BAR_OFF = STAGES * SLOT_BYTES + SRING_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + (STAGES + SSTAGES) * 8;
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
@@ -95,16 +100,24 @@ __device__ __forceinline__ void zfix(F4& a, bool lo2, bool hi2) {
     if (hi2) a.v[3] = a.v[2];
 }
 
-template <int MODEL, bool HET, int MATH, bool HAS_X, int R>
+struct StateMaps {
+    CUtensorMap m[PDX_MAX_STATES];
+};
+
+// TST: the state arrays are staged through shared memory by TMA (SSTAGES planes ahead) instead of
+// being prefetched one plane ahead in registers
+template <int MODEL, bool HET, int MATH, bool HAS_X, int R, bool TST>
 __global__ void __launch_bounds__(NTHREADS, (R == 1 && !HET) ? 3 : 2)
 fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD,
-              const __grid_constant__ FdArgs a) {
-    using G = Geo<R, HET>;
+              const __grid_constant__ StateMaps mapS, const __grid_constant__ FdArgs a) {
     constexpr int NS = NStates<MODEL>::value;
+    using G = Geo<R, HET, TST ? NS : 0>;
     constexpr int TY = G::TY;
     constexpr int NSTAGE = STAGES;
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * G::SLOT_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
+    uint64_t* sfull = full + NSTAGE;
+    unsigned char* sring = smem + NSTAGE * G::SLOT_BYTES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int b = blockIdx.x;
@@ -127,16 +140,30 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
         if (HET) tma_load_3d(slotD(j), &mapD, z0 - ZH, y0 - 1, HAS_X ? clampi(q, a.dxlo, a.dxhi) : q, bar);
     };
     auto wait_plane = [&](int j) { mbar_wait(&full[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1)); };
+    auto sslot = [&](int i, int s) {
+        return reinterpret_cast<float*>(sring + ((i % SSTAGES) * (NS > 0 ? NS : 1) + s) * G::ST_BYTES);
+    };
+    auto issue_states = [&](int i) {   // thread 0 only; plane xb + i
+        uint64_t* bar = &sfull[i % SSTAGES];
+        mbar_expect_tx(bar, NS * G::ST_BYTES);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) tma_load_3d(sslot(i, s), &mapS.m[s], z0, y0, xb + i, bar);
+    };
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+#pragma unroll
+        for (int s = 0; s < SSTAGES; ++s) mbar_init(&sfull[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
     if (tid == 0) {
         const int n0 = min(NSTAGE, nlog);
-        for (int j = 0; j < n0; ++j) issue(j);
+        for (int j = 0; j < n0; ++j) {
+            issue(j);
+            if (TST && NS > 0 && j < SSTAGES && j < np) issue_states(j);
+        }
     }
 
     // ---- per-thread geometry (constant along the march) ----
@@ -175,7 +202,10 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             for (int s = 0; s < NS; ++s) stn[r][s] = ldg4(a.st[s] + gi);
         }
     };
-    if (NS > 0 && np > 0) load_states(xb);
+    if (!TST && NS > 0 && np > 0) load_states(xb);
+    int srow[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) srow[r] = (warp * R + r) * TZ + 4 * lane;
 
     for (int i = 0; i < np; ++i) {
         const int p = xb + i;
@@ -192,11 +222,21 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
         const bool raw_diff = yb_tile || zb_tile || (HAS_X && (p < a.xclo || p > a.xchi));   // CTA uniform
 
         F4 stc[R][NS > 0 ? NS : 1];
+        if (TST) {
+            if (NS > 0) {
+                mbar_wait(&sfull[i % SSTAGES], (uint32_t)((i / SSTAGES) & 1));
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+                for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int s = 0; s < NS; ++s) stc[r][s] = stn[r][s];
-        if (NS > 0 && i + 1 < np) load_states(p + 1);
+                    for (int s = 0; s < NS; ++s) stc[r][s] = lds4(sslot(i, s) + srow[r]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int s = 0; s < NS; ++s) stc[r][s] = stn[r][s];
+            if (NS > 0 && i + 1 < np) load_states(p + 1);
+        }
 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -266,14 +306,17 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             for (int s = 0; s < NS; ++s) stg4(a.st[s] + gi, stc[r][s]);
         }
         __syncthreads();                              // everyone is done with logical plane i
-        if (tid == 0 && i + NSTAGE < nlog) issue(i + NSTAGE);
+        if (tid == 0) {
+            if (i + NSTAGE < nlog) issue(i + NSTAGE);
+            if (TST && NS > 0 && i + SSTAGES < np) issue_states(i + SSTAGES);
+        }
     }
 }
 
-template <int MODEL, bool HET, int MATH, bool HAS_X, int R>
-int launch_inst(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
-    using G = Geo<R, HET>;
-    auto kern = fd_tma_kernel<MODEL, HET, MATH, HAS_X, R>;
+template <int MODEL, bool HET, int MATH, bool HAS_X, int R, bool TST>
+int launch_inst(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, const StateMaps& mS, cudaStream_t s) {
+    using G = Geo<R, HET, TST ? NStates<MODEL>::value : 0>;
+    auto kern = fd_tma_kernel<MODEL, HET, MATH, HAS_X, R, TST>;
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
         if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES),
@@ -286,24 +329,34 @@ int launch_inst(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, c
     const int nchunk = (nplanes + a.x_chunk - 1) / a.x_chunk;
     const long long nb = (long long)a.ntz * a.nty * nchunk;
     if (nb > 0x7fffffffLL) { set_error("fd_tma: grid too large"); return 1; }
-    kern<<<(unsigned)nb, NTHREADS, G::SMEM_BYTES, s>>>(mU, mD, a);
+    kern<<<(unsigned)nb, NTHREADS, G::SMEM_BYTES, s>>>(mU, mD, mS, a);
     count_launch();
     return check_cuda(cudaGetLastError(), "fd_tma_kernel launch");
 }
 
+template <int MODEL, bool HET, int MATH, bool TST>
+int launch_hasx(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, const StateMaps& mS, cudaStream_t s) {
+    return a.has_x ? launch_inst<MODEL, HET, MATH, true, 1, TST>(a, mU, mD, mS, s)
+                   : launch_inst<MODEL, HET, MATH, false, 1, TST>(a, mU, mD, mS, s);
+}
 template <int MODEL, bool HET, int MATH>
-int launch_hasx(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
-    return a.has_x ? launch_inst<MODEL, HET, MATH, true, 1>(a, mU, mD, s)
-                   : launch_inst<MODEL, HET, MATH, false, 1>(a, mU, mD, s);
+int launch_tst(bool tst, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, const StateMaps& mS,
+               cudaStream_t s) {
+    if (NStates<MODEL>::value == 0) tst = false;
+    return tst ? launch_hasx<MODEL, HET, MATH, true>(a, mU, mD, mS, s)
+               : launch_hasx<MODEL, HET, MATH, false>(a, mU, mD, mS, s);
 }
 template <int MODEL, bool HET>
-int launch_math(int math, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
-    return math == PDX_MATH_EXACT ? launch_hasx<MODEL, HET, PDX_MATH_EXACT>(a, mU, mD, s)
-                                  : launch_hasx<MODEL, HET, PDX_MATH_FAST>(a, mU, mD, s);
+int launch_math(int math, bool tst, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD,
+                const StateMaps& mS, cudaStream_t s) {
+    return math == PDX_MATH_EXACT ? launch_tst<MODEL, HET, PDX_MATH_EXACT>(tst, a, mU, mD, mS, s)
+                                  : launch_tst<MODEL, HET, PDX_MATH_FAST>(tst, a, mU, mD, mS, s);
 }
 template <int MODEL>
-int launch_het(bool het, int math, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, cudaStream_t s) {
-    return het ? launch_math<MODEL, true>(math, a, mU, mD, s) : launch_math<MODEL, false>(math, a, mU, mD, s);
+int launch_het(bool het, int math, bool tst, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD,
+               const StateMaps& mS, cudaStream_t s) {
+    return het ? launch_math<MODEL, true>(math, tst, a, mU, mD, mS, s)
+               : launch_math<MODEL, false>(math, tst, a, mU, mD, mS, s);
 }
 
 }  // namespace
@@ -314,6 +367,11 @@ bool fd_tma_supported(const pdx_fd_desc& d) {
     if (d.lap_kind == PDX_LAP_CONV && d.math_mode == PDX_MATH_EXACT) return false;   // different rounding order
     if (d.ny < 3) return false;
     return true;
+}
+
+void fd_tma_state_box(int* box_y, int* box_z) {
+    *box_y = NWARP * 1;
+    *box_z = TZ;
 }
 
 void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* box_y, int* box_z) {
@@ -340,13 +398,19 @@ int fd_tma_auto_chunk(const pdx_fd_desc& d) {
 }
 
 int launch_fd_tma(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD,
-                  cudaStream_t s) {
+                  const CUtensorMap* const* mS, cudaStream_t s) {
     const bool het = d.lap_kind == PDX_LAP_HETEROG;
+    StateMaps sm;
+    bool tst = mS != nullptr;
+    for (int i = 0; i < PDX_MAX_STATES; ++i) {
+        if (tst && mS[i]) sm.m[i] = *mS[i];
+        else sm.m[i] = mU;
+    }
     switch (d.model) {
-        case PDX_MODEL_NONE:     return launch_het<PDX_MODEL_NONE>(het, d.math_mode, a, mU, mD, s);
-        case PDX_MODEL_FENTON4V: return launch_het<PDX_MODEL_FENTON4V>(het, d.math_mode, a, mU, mD, s);
-        case PDX_MODEL_MMS2V:    return launch_het<PDX_MODEL_MMS2V>(het, d.math_mode, a, mU, mD, s);
-        case PDX_MODEL_MS2V:     return launch_het<PDX_MODEL_MS2V>(het, d.math_mode, a, mU, mD, s);
+        case PDX_MODEL_NONE:     return launch_het<PDX_MODEL_NONE>(het, d.math_mode, tst, a, mU, mD, sm, s);
+        case PDX_MODEL_FENTON4V: return launch_het<PDX_MODEL_FENTON4V>(het, d.math_mode, tst, a, mU, mD, sm, s);
+        case PDX_MODEL_MMS2V:    return launch_het<PDX_MODEL_MMS2V>(het, d.math_mode, tst, a, mU, mD, sm, s);
+        case PDX_MODEL_MS2V:     return launch_het<PDX_MODEL_MS2V>(het, d.math_mode, tst, a, mU, mD, sm, s);
     }
     set_error("unknown model");
     return 1;

@@ -68,8 +68,11 @@ int launch_lut_ionic(int model, const LutArgs& L, int64_t n, const float* U, flo
 int launch_fd_lut(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s);
 // TMA-staged tile kernel: requires nz % 4 == 0, 16-byte aligned arrays, HOMOG/HETEROG
 bool fd_tma_supported(const pdx_fd_desc& d);
+// mapS: per-state tensor maps (box = fd_tma_state_box) to stage the states by TMA, or nullptr to
+// prefetch them in registers
 int  launch_fd_tma(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mapU, const CUtensorMap& mapD,
-                   cudaStream_t s);
+                   const CUtensorMap* const* mapS, cudaStream_t s);
+void fd_tma_state_box(int* box_y, int* box_z);
 int  make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int nz, int box_x, int box_y,
                         int box_z);
 // geometry of the TMA kernel's tile, needed by the host to build the tensor maps
