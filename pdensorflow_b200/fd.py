@@ -335,3 +335,54 @@ class DistributedFDStepper:
 
     def owned_U(self):
         return self.part.owned(self.fd.current_U())
+
+
+class FramePipeline:
+    """End-to-end frame loop over host buffers, pipelined across independent simulations.
+
+    Each simulation keeps the reference's per-frame dataflow (``Tests/FD/Fenton/fenton.py:150-159``:
+    advance ``dt_per_plot`` steps, hand the potential to the writer) but through HOST memory: its
+    potential is uploaded from a pinned host buffer, advanced ``steps_per_frame`` fused steps (one
+    CUDA graph), and downloaded back into the same pinned buffer.  With several simulations (an
+    ensemble / parameter sweep) in flight the three engines overlap: while one simulation
+    computes, another one's frame is on its way down and a third one's input on its way up
+    (H2D stream, compute stream, D2H stream; dependencies are CUDA events, no host sync inside).
+    """
+
+    def __init__(self, steppers, steps_per_frame=10):
+        self.sims = list(steppers)
+        self.steps = int(steps_per_frame)
+        dev = self.sims[0].device
+        self.h2d, self.comp, self.d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.host = [torch.empty(s.array_shape, dtype=torch.float32, pin_memory=True) for s in self.sims]
+        for h, s in zip(self.host, self.sims):
+            h.copy_(s.U())
+            s.capture(self.steps + self.steps % 2)
+        torch.cuda.synchronize(dev)
+        self._up = [torch.cuda.Event() for _ in self.sims]
+        self._done = [torch.cuda.Event() for _ in self.sims]
+        self._down = [torch.cuda.Event() for _ in self.sims]
+        self._first = True
+        self.frame_bytes = self.host[0].numel() * 4
+
+    def frame(self):
+        """One frame of every simulation (enqueue only)."""
+        for k, s in enumerate(self.sims):
+            with torch.cuda.stream(self.h2d):
+                if not self._first:
+                    self.h2d.wait_event(self._down[k])       # the host buffer holds the previous frame
+                s.current_U().copy_(self.host[k], non_blocking=True)
+                self._up[k].record(self.h2d)
+            with torch.cuda.stream(self.comp):
+                self.comp.wait_event(self._up[k])
+                s.run(self.steps, block=self.steps)
+                self._done[k].record(self.comp)
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(self._done[k])
+                self.host[k].copy_(s.current_U(), non_blocking=True)
+                self._down[k].record(self.d2h)
+        self._first = False
+
+    def wait(self):
+        for st in (self.h2d, self.comp, self.d2h):
+            st.synchronize()
