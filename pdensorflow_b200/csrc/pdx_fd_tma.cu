@@ -383,16 +383,15 @@ void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* b
 }
 
 int fd_tma_auto_chunk(const pdx_fd_desc& d) {
-    // enough CTAs for >= ~10 waves of 148 SMs x 3 CTAs, but at least 8 planes per CTA so the
-    // two extra halo planes per chunk stay a small fraction of the U traffic
+    // Planes marched per CTA.  Measured on B200 (tools/chunk_sweep.py, 512^3 and 128x2048^2): the
+    // optimum is flat at 6-8 planes - short chunks keep several x-layers of CTAs resident at once,
+    // so the two halo planes each chunk re-reads are L2 hits, and the grid has thousands of CTAs to
+    // balance over 148 SMs x 3.  Small grids shorten the chunk further to keep >= 2 waves of CTAs.
     const int nplanes = d.x_end - d.x_begin;
     if (d.ndim == 2 || nplanes <= 1) return 1;
     const long long tiles = (long long)((d.ny + NWARP - 1) / NWARP) * ((d.nz + TZ - 1) / TZ);
-    const long long want = 148LL * 3 * 10;
-    long long nchunk = (want + tiles - 1) / tiles;
-    if (nchunk < 1) nchunk = 1;
-    int chunk = (int)((nplanes + nchunk - 1) / nchunk);
-    if (chunk < 8) chunk = 8;
+    int chunk = 8;
+    while (chunk > 3 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * 3 * 2) --chunk;
     if (chunk > nplanes) chunk = nplanes;
     return chunk;
 }
