@@ -244,7 +244,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = hbm_peak()
         # dominant kernel: fd_tma_kernel, one launch per time step per rank
-        launches_per_rank = STEPS_PER_FRAME * args.steps * (1 if world == 1 else 3)
+        launches_per_rank = STEPS_PER_FRAME * args.steps * (1 if world == 1 else ds.launches_per_step())
         step_ms = ms / (STEPS_PER_FRAME * args.steps)
         achieved = nodes_local * BYTES_PER_NODE_STEP / (step_ms * 1e-3) / 1e9
         tr = ncu_traffic() if world == 1 else None      # the committed capture is the 512^3 launch
@@ -258,7 +258,10 @@ def run_ours(args):
                        'arithmetic': 'FAST (rel-L2 <= 1e-5 vs oracle, tests/test_fd_gpu.py)', 'kernel': fd.kernel,
                        'cache': 'inputs larger than L2: %.2f GB of state per GPU vs 126 MB L2' %
                                 (nodes_local * 20 / 1e9),
-                       'parallelism': 'single GPU' if world == 1 else 'x-slab x%d, 1-plane NCCL halo per step' % world},
+                       'parallelism': 'single GPU' if world == 1 else
+                       ('x-slab x%d, halo planes stored into the neighbours\' ghost planes by the step kernel over NVLink '
+                        'peer memory, one symmetric-memory barrier per step' % world if ds.halo == 'peer' else
+                        'x-slab x%d, 1-plane NCCL halo per step' % world)},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'Gnode-steps/s', 'h2d_bytes_per_step': frame_bytes,
                     'd2h_bytes_per_step': frame_bytes, 'steps': ke,

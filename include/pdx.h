@@ -171,6 +171,16 @@ int pdx_fd_plan_set_avec(pdx_fd_plan* p, const float* AVEC);
 int pdx_fd_step_range(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states,
                       const float* DIFF, int xb, int xe, void* stream);
 
+/* One full step of a slab with the halo exchange FUSED into it: besides U_out, the new values of
+ * the slab's first owned plane (x_begin) are stored to mirror_lo and those of its last owned plane
+ * (x_end - 1) to mirror_hi - plane-sized ([ny][nz]) buffers that are the neighbouring ranks' ghost
+ * planes, mapped into this process as NVLink peer memory (CUDA IPC / symmetric memory).  Either
+ * may be NULL (global boundary).  The caller orders steps across ranks with one barrier per step
+ * (pdensorflow_b200.fd.DistributedFDStepper, halo='peer').  New functionality: the reference has
+ * no multi-GPU path. */
+int pdx_fd_step_mirror(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states,
+                       const float* DIFF, float* mirror_lo, float* mirror_hi, void* stream);
+
 /* Stand-alone operators (pure functions, new output array) - contract 1:
  * gpuSolve/diffop3D/laplace_homogeneous_isotropic_diffusion.py:3-52,
  * laplace_convolution_homogeneous_isotropic_diffusion.py:4-47,

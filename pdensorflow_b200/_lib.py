@@ -63,6 +63,7 @@ _SIGNATURES = {
     'pdx_fd_plan_kernel': (C.c_int, [_P]),
     'pdx_fd_plan_launches': (C.c_int64, [_P]),
     'pdx_fd_step': (C.c_int, [_P, _P, _P, C.POINTER(_P), _P, C.c_int, _P]),
+    'pdx_fd_step_mirror': (C.c_int, [_P, _P, _P, C.POINTER(_P), _P, _P, _P, _P]),
     'pdx_fd_step_range': (C.c_int, [_P, _P, _P, C.POINTER(_P), _P, C.c_int, C.c_int, _P]),
     'pdx_fd_laplace': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                  C.c_int, C.c_int, _P, _P, _P, _P]),

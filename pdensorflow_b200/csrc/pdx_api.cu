@@ -317,7 +317,7 @@ int pdx_fd_plan_kernel(const pdx_fd_plan* p) { return p ? p->kernel : -1; }
 int64_t pdx_fd_plan_launches(const pdx_fd_plan* p) { return p ? p->launches : -1; }
 
 static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const* states, const float* DIFF, int xb,
-                     int xe, cudaStream_t s) {
+                     int xe, cudaStream_t s, float* mirror_lo = nullptr, float* mirror_hi = nullptr) {
     const pdx_fd_desc& d = p->d;
     if (!Uin || !Uout || Uin == Uout) { set_error("pdx_fd_step: U_in/U_out must be distinct non-null buffers"); return 1; }
     const int ns = pdx_model_num_states(d.model);
@@ -329,6 +329,8 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
     if (d.lap_kind == PDX_LAP_ANISO && !p->avec) { set_error("pdx_fd_step: call pdx_fd_plan_set_avec first"); return 1; }
     FdArgs a = p->base;
     a.Uin = Uin; a.Uout = Uout; a.DIFF = DIFF; a.AVEC = p->avec;
+    a.mirror_lo = mirror_lo; a.mirror_hi = mirror_hi;
+    a.mirror_lo_plane = d.x_begin; a.mirror_hi_plane = d.x_end - 1;
     const bool lut = is_lut_model(d.model);
     if (lut && !p->has_lut) { set_error("pdx_fd_step: call pdx_fd_plan_set_lut first"); return 1; }
     for (int i = 0; i < ns; ++i) {
@@ -390,6 +392,14 @@ int pdx_fd_step(pdx_fd_plan* p, float* U_a, float* U_b, float* const* states, co
         if (step_once(p, in, outp, states, DIFF, p->d.x_begin, p->d.x_end, (cudaStream_t)stream)) return 1;
     }
     return 0;
+}
+
+int pdx_fd_step_mirror(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states, const float* DIFF,
+                       float* mirror_lo, float* mirror_hi, void* stream) {
+    if (!p) { set_error("pdx_fd_step_mirror: null plan"); return 1; }
+    if (p->d.ndim != 3) { set_error("pdx_fd_step_mirror: slab decomposition is 3-D only"); return 1; }
+    if (((uintptr_t)mirror_lo | (uintptr_t)mirror_hi) % 16 != 0) { set_error("pdx_fd_step_mirror: mirror planes must be 16-byte aligned"); return 1; }
+    return step_once(p, U_in, U_out, states, DIFF, p->d.x_begin, p->d.x_end, (cudaStream_t)stream, mirror_lo, mirror_hi);
 }
 
 int pdx_fd_step_range(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states, const float* DIFF,

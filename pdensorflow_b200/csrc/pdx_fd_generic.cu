@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(256) fd_generic_kernel(const __grid_constant__
         for (int s = 0; s < NS; ++s) a.st[s][idx] = st[s];
         u1 = madd<MATH>(u1, mmul<MATH>(a.dt, dU));
     }
-    a.Uout[idx] = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
+    const float u_new = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
+    a.Uout[idx] = u_new;
+    if (a.mirror_lo && i == a.mirror_lo_plane) a.mirror_lo[(size_t)j * a.nz + k] = u_new;
+    if (a.mirror_hi && i == a.mirror_hi_plane) a.mirror_hi[(size_t)j * a.nz + k] = u_new;
 }
 
 template <int MODEL, int LAP, int MATH, int MODE>

@@ -302,6 +302,10 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
                 out.v[e] = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
             }
             stg4(a.Uout + gi, out);
+            if (HAS_X) {   // fused halo store into the neighbours' ghost planes (peer memory over NVLink)
+                if (a.mirror_lo && p == a.mirror_lo_plane) stg4(a.mirror_lo + (size_t)gy[r] * a.nz + z, out);
+                if (a.mirror_hi && p == a.mirror_hi_plane) stg4(a.mirror_hi + (size_t)gy[r] * a.nz + z, out);
+            }
 #pragma unroll
             for (int s = 0; s < NS; ++s) stg4(a.st[s] + gi, stc[r][s]);
         }

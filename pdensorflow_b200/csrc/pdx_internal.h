@@ -16,6 +16,12 @@ struct FdArgs {
     float*       st[PDX_MAX_STATES];
     const float* DIFF;
     const float* AVEC;           // fibre dyadic [nx][ny][nz][6] (ANISO)
+    // fused halo store (slab decomposition over NVLink peer memory): the output of plane
+    // mirror_lo_plane / mirror_hi_plane is ALSO stored to these plane-sized peer buffers (the
+    // neighbours' ghost planes); nullptr = off
+    float* mirror_lo;
+    float* mirror_hi;
+    int mirror_lo_plane, mirror_hi_plane;
     int nx, ny, nz;
     int xb, xe;                  // planes advanced
     int xclo, xchi;              // clamp of stencil plane indices for U (enforce_boundary + pad)

@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(128) lut_fd_kernel(const __grid_constant__ FdA
     float c;
     const float lap = node_laplacian<LAP, PDX_MATH_EXACT>(a, f, i, j, k, c);
     const float dU = lut_update<MODEL>(L, idx, a.Uin[idx]);      // raw U, not U0
-    a.Uout[idx] = (c + a.dt * dU) + a.coef * lap;
+    const float u_new = (c + a.dt * dU) + a.coef * lap;
+    a.Uout[idx] = u_new;
+    if (a.mirror_lo && i == a.mirror_lo_plane) a.mirror_lo[(size_t)j * a.nz + k] = u_new;
+    if (a.mirror_hi && i == a.mirror_hi_plane) a.mirror_hi[(size_t)j * a.nz + k] = u_new;
 }
 
 template <int MODEL>

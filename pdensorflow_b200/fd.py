@@ -102,7 +102,7 @@ class FDStepper:
     """
 
     def __init__(self, shape, spacing, dt, diff=1.0, model='fenton4v', params=None, lap='homog', DIFF=None,
-                 math='fast', kernel='auto', part=None, device=None, x_chunk=0, AVEC=None):
+                 math='fast', kernel='auto', part=None, device=None, x_chunk=0, AVEC=None, buffers=None):
         self.device = torch.device('cuda' if device is None else device)
         if self.device.type != 'cuda':
             raise L.PdxError('FDStepper needs a CUDA device: there is no CPU path')
@@ -155,8 +155,14 @@ class FDStepper:
         self.dt, self.diff = dt, diff
         self.nstates = L.lib().pdx_model_num_states(self.model_id)
         # buffers
-        self.Ua = torch.empty(self.array_shape, dtype=torch.float32, device=self.device)
-        self.Ub = torch.empty_like(self.Ua)
+        if buffers is not None:      # caller-owned ping-pong pair (e.g. NVLink symmetric memory)
+            self.Ua, self.Ub = buffers
+            for b in (self.Ua, self.Ub):
+                if tuple(b.shape) != tuple(self.array_shape) or b.dtype != torch.float32 or not b.is_contiguous():
+                    raise ValueError('buffers must be contiguous fp32 tensors of the array shape')
+        else:
+            self.Ua = torch.empty(self.array_shape, dtype=torch.float32, device=self.device)
+            self.Ub = torch.empty_like(self.Ua)
         if self.is_lut:
             # the model instance owns tables, constants and the 19/22 state arrays
             self.ionic._dt = dt
@@ -285,20 +291,57 @@ class FDStepper:
 
 
 class DistributedFDStepper:
-    """Slab-decomposed 3-D stepping: one process per GPU, NCCL halo exchange.
+    """Slab-decomposed 3-D stepping: one process per GPU.
 
-    Per step: (1) the two slab-boundary planes are advanced first, (2) their exchange with
-    the neighbours runs on a side stream while (3) the interior planes are advanced on the
-    main stream; the next step starts when both are done.
+    halo='peer' (default on CUDA when torch symmetric memory is available): the two U buffers live
+    in NVLink symmetric memory; ONE kernel per step advances the whole slab and, fused into it,
+    stores its first/last owned planes straight into the neighbours' ghost planes over NVLink
+    (``pdx_fd_step_mirror``); one symmetric-memory barrier (~6 us) per step orders the ranks.  No
+    NCCL kernel, no separate boundary launches, nothing to overlap.
+    Why one barrier suffices: step k reads buffer A and writes B (+ the neighbours' B ghosts).  The
+    barrier after step k guarantees (i) every B ghost is complete before any rank's step k+1 reads
+    it, and (ii) every rank has finished reading A before a neighbour's step k+1 overwrites its A ghost.
+
+    halo='nccl': per step the two slab-boundary planes are advanced first, their exchange with the
+    neighbours (batch_isend_irecv) runs on a side stream while the interior planes are advanced.
     """
 
-    def __init__(self, global_shape, spacing, dt, diff=1.0, rank=0, world=1, group=None, overlap=True, **kw):
+    def __init__(self, global_shape, spacing, dt, diff=1.0, rank=0, world=1, group=None, overlap=True, halo='auto',
+                 **kw):
         self.part = SlabPartition(global_shape[0], rank, world)
         self.group = group
         self.overlap = overlap and world > 1
-        self.fd = FDStepper(global_shape, spacing, dt, diff, part=self.part, **kw)
-        self.comm_stream = torch.cuda.Stream(device=self.fd.device) if world > 1 else None
+        self.world, self.rank = world, rank
+        self.halo = 'nccl'
+        buffers = None
+        if world > 1 and halo in ('auto', 'peer'):
+            try:
+                buffers = self._alloc_symmetric(global_shape, kw.get('device'))
+                self.halo = 'peer'
+            except Exception:
+                if halo == 'peer':
+                    raise
+        self.fd = FDStepper(global_shape, spacing, dt, diff, part=self.part, buffers=buffers, **kw)
+        self.comm_stream = torch.cuda.Stream(device=self.fd.device, priority=-1) if world > 1 else None
         self._ev = torch.cuda.Event()
+        self._primed = False
+        if self.halo == 'peer':
+            p = self.part
+            plane_bytes = self.fd.array_shape[1] * self.fd.array_shape[2] * 4
+            nloc_lo = SlabPartition(global_shape[0], rank - 1, world).nloc if p.lo_rank is not None else 0
+            # [buffer index] -> device address of the neighbour's ghost plane that mirrors my edge plane
+            self._mirror_lo = [None if p.lo_rank is None else h.buffer_ptrs[p.lo_rank] + (nloc_lo + 1) * plane_bytes
+                               for h in self._hdl]
+            self._mirror_hi = [None if p.hi_rank is None else h.buffer_ptrs[p.hi_rank] for h in self._hdl]
+
+    def _alloc_symmetric(self, global_shape, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        shape = (self.part.nx_array, global_shape[1], global_shape[2])
+        bufs = [symm.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self._hdl = [symm.rendezvous(b, self.group if self.group is not None else dist.group.WORLD) for b in bufs]
+        return bufs
 
     def set_global(self, U, states=None, DIFF=None):
         """Install this rank's slab of global NumPy fields (ghost planes included)."""
@@ -307,31 +350,54 @@ class DistributedFDStepper:
             self.fd.set_states([self.part.scatter(s) for s in states])
         if DIFF is not None:
             self.fd.DIFF.copy_(self.fd._to_device(self.part.scatter(DIFF)))
+        self._primed = False
 
     def exchange(self, U):
         return exchange_halos(U, self.part, self.group)
 
+    def _prime(self):
+        """Make the current buffer's ghost planes valid and line the ranks up before the first step."""
+        self.exchange(self.fd.current_U())
+        if self.halo == 'peer':
+            self._hdl[0].barrier(channel=0)
+        self._primed = True
+
     def step(self, nsteps=1):
         fd, p = self.fd, self.part
+        if p.world > 1 and not self._primed:
+            self._prime()
         for _ in range(nsteps):
             if p.world == 1:
                 fd.step(1)
                 continue
             out = fd.other_U()
             main = torch.cuda.current_stream(fd.device)
-            if self.overlap and p.nloc >= 3:
+            if self.halo == 'peer':
+                oi = 0 if out is fd.Ua else 1
+                L.check(L.lib().pdx_fd_step_mirror(fd._plan, L.ptr(fd.current_U()), L.ptr(out), fd._states_arr,
+                                                   L.ptr(fd.DIFF), C.c_void_p(self._mirror_lo[oi]),
+                                                   C.c_void_p(self._mirror_hi[oi]), L.stream_ptr(main)))
+                self._hdl[0].barrier(channel=0)
+            elif self.overlap and p.nloc >= 3:
                 fd.step_range(p.x_begin, p.x_begin + 1)
                 fd.step_range(p.x_end - 1, p.x_end)
                 self._ev.record(main)
+                # the interior is enqueued BEFORE the (CPU-expensive) NCCL calls so that the GPU never
+                # idles between the boundary planes and the interior while the host issues the exchange
+                fd.step_range(p.x_begin + 1, p.x_end - 1)
                 with torch.cuda.stream(self.comm_stream):
                     self.comm_stream.wait_event(self._ev)
                     self.exchange(out)
-                fd.step_range(p.x_begin + 1, p.x_end - 1)
                 main.wait_stream(self.comm_stream)
             else:
                 fd.step_range(p.x_begin, p.x_end)
                 self.exchange(out)
             fd.swap()
+
+    def launches_per_step(self):
+        if self.part.world == 1 or self.halo == 'peer':
+            return 1
+        return 3 if (self.overlap and self.part.nloc >= 3) else 1
 
     def owned_U(self):
         return self.part.owned(self.fd.current_U())

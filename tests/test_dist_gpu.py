@@ -1,5 +1,7 @@
-"""Slab-decomposed stepping on >= 2 GPUs (NCCL halo exchange) must equal the single-GPU run
-bit for bit in EXACT arithmetic (same per-node operations).  Skipped on a 1-GPU box."""
+"""Slab-decomposed stepping on >= 2 GPUs must equal the single-GPU run bit for bit in EXACT
+arithmetic (same per-node operations), for both halo transports: 'peer' (halo stores fused into the
+step kernel over NVLink symmetric memory + one barrier per step) and 'nccl' (send/recv, overlapped
+or not).  Skipped on a 1-GPU box."""
 import os
 import socket
 
@@ -11,7 +13,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, shape, nsteps, overlap, q):
+def _worker(rank, world, port, shape, nsteps, overlap, halo, q):
     import torch.distributed as dist
     from pdensorflow_b200.fd import DistributedFDStepper
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -22,8 +24,9 @@ def _worker(rank, world, port, shape, nsteps, overlap, q):
         rng = np.random.default_rng(0)
         G = rng.uniform(-85, 25, size=shape).astype(np.float32)
         S = [rng.uniform(0, 1, size=shape).astype(np.float32) for _ in range(3)]
-        ds = DistributedFDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8, rank=rank, world=world, overlap=overlap,
+        ds = DistributedFDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8, rank=rank, world=world, overlap=overlap, halo=halo,
                                   model='fenton4v', math='exact', device=torch.device('cuda', rank))
+        assert ds.halo == halo
         ds.set_global(G, S)
         ds.step(nsteps)
         torch.cuda.synchronize()
@@ -33,18 +36,19 @@ def _worker(rank, world, port, shape, nsteps, overlap, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('overlap', [True, False])
-def test_two_gpu_slabs_match_single_gpu(cuda, overlap):
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs 2 GPUs')
+@pytest.mark.parametrize('halo,overlap,world', [('peer', True, 2), ('nccl', True, 2), ('nccl', False, 2), ('peer', True, 3),
+                                                ('peer', True, 8)])
+def test_multi_gpu_slabs_match_single_gpu(cuda, halo, overlap, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
     from pdensorflow_b200.fd import FDStepper
-    world, shape, nsteps = 2, (22, 24, 132), 7
+    shape, nsteps = (22 if world == 2 else 37, 24, 132), 7
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, nsteps, overlap, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, nsteps, overlap, halo, q)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(world)]

@@ -28,7 +28,7 @@ if world == 1:
         del st
 else:
     for overlap in (True, False):
-        ds = DistributedFDStepper(G, (1., 1., 1.), 0.1, 0.8, rank=rank, world=world, overlap=overlap)
+        ds = DistributedFDStepper(G, (1., 1., 1.), 0.1, 0.8, rank=rank, world=world, overlap=overlap, halo="nccl" if not overlap else "peer")
         ds.fd.U().fill_(-80.)
         t = timeit(lambda: ds.step(1))
         fd, p = ds.fd, ds.part
