@@ -242,6 +242,19 @@ int pdx_fem_explicit_step(int model, int math_mode, const float* params, int32_t
                           const float* mlinv, const float* U_in, float* U_out,
                           float* const* states, const float* I0, float dt, void* stream);
 
+/* Row-block partitioned form of the same step (config 5: node-block partition with ghost-node
+ * exchange).  This rank owns global rows [row_lo, row_lo + n_local); rowptr is local, col holds
+ * GLOBAL column indices; U_in / U_out are full-length (global) buffers of which the rank's own rows
+ * and its ghost columns are valid; states, mlinv and I0 are local (n_local).  The new values of the
+ * first send_lo and last send_hi local rows are also stored at their global index into mirror_lo /
+ * mirror_hi = the neighbouring ranks' U_out buffers mapped as NVLink peer memory, i.e. the ghost
+ * exchange is fused into the step; the caller orders steps with one barrier per step
+ * (pdensorflow_b200.fem_dist.PartitionedExplicitFEM). */
+int pdx_fem_explicit_step_part(int model, int math_mode, const float* params, int32_t n_local, int32_t row_lo,
+                               const int32_t* rowptr, const int32_t* col, const float* kval, const float* mlinv,
+                               const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
+                               int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream);
+
 /* ------------------------------------------------------------------ misc */
 int         pdx_version(void);
 const char* pdx_last_error(void);

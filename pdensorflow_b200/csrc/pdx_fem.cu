@@ -198,8 +198,15 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
 }
 
 // ---------------------------------------------------------------- explicit lumped step
+// Rows are LOCAL (0..n-1) and belong to global rows row_lo..row_lo+n-1 of a row-block partition;
+// columns, U_in and U_out are GLOBAL (every rank holds full-length U buffers of which only its own
+// rows and its ghost columns are valid); states, mlinv and I0 are local.  The new values of the
+// first send_lo / last send_hi local rows are also stored into the neighbouring ranks' U_out
+// buffers (NVLink peer memory) at the same global index: the ghost exchange is fused into the step.
+// A non-partitioned call is row_lo = 0 with no mirrors.
 struct ExplArgs {
     int n;
+    int row_lo;
     const int32_t* rowptr;
     const int32_t* col;
     const float* kval;
@@ -208,6 +215,9 @@ struct ExplArgs {
     float* Uout;
     float* st[PDX_MAX_STATES];
     const float* I0;
+    float* mirror_lo;
+    float* mirror_hi;
+    int send_lo, send_hi;
     ModelParams mp;
 };
 
@@ -223,7 +233,8 @@ __global__ void __launch_bounds__(256) fem_explicit_kernel(const __grid_constant
         const float ku = row_dot<G>(a.col, a.kval, a.Uin, valid ? a.rowptr[row] : 0, valid ? a.rowptr[row + 1] : 0,
                                     sub, false);
         if (valid && sub == 0) {
-            const float U = a.Uin[row];
+            const size_t grow = (size_t)a.row_lo + row;
+            const float U = a.Uin[grow];
             float st[PDX_MAX_STATES];
 #pragma unroll
             for (int s = 0; s < NS; ++s) st[s] = a.st[s][row];
@@ -232,7 +243,10 @@ __global__ void __launch_bounds__(256) fem_explicit_kernel(const __grid_constant
             for (int s = 0; s < NS; ++s) a.st[s][row] = st[s];
             if (a.I0) dU += a.I0[row];
             // U1 = U + dt*(dU + I0) - dt*mlinv*(K U)
-            a.Uout[row] = fmaf(-a.mp.dt * a.mlinv[row], ku, fmaf(a.mp.dt, dU, U));
+            const float u1 = fmaf(-a.mp.dt * a.mlinv[row], ku, fmaf(a.mp.dt, dU, U));
+            a.Uout[grow] = u1;
+            if (a.mirror_lo && row < a.send_lo) a.mirror_lo[grow] = u1;
+            if (a.mirror_hi && row >= a.n - a.send_hi) a.mirror_hi[grow] = u1;
         }
     }
 }
@@ -354,20 +368,41 @@ int pdx_pcg_solve(pdx_pcg* s, const float* b, float* x, int maxiter, double toll
                       "pcg_kernel cooperative launch");
 }
 
-int pdx_fem_explicit_step(int model, int math_mode, const float* params, int32_t n, const int32_t* rowptr,
-                          const int32_t* col, const float* kval, const float* mlinv, const float* U_in, float* U_out,
-                          float* const* states, const float* I0, float dt, void* stream) {
-    if (n <= 0 || !rowptr || !col || !kval || !mlinv || !U_in || !U_out || U_in == U_out) {
+static int explicit_step_impl(int model, int math_mode, const float* params, int32_t n, int32_t row_lo,
+                              const int32_t* rowptr, const int32_t* col, const float* kval, const float* mlinv,
+                              const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
+                              int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream) {
+    if (n <= 0 || row_lo < 0 || !rowptr || !col || !kval || !mlinv || !U_in || !U_out || U_in == U_out) {
         set_error("pdx_fem_explicit_step: bad arguments");
         return 1;
     }
+    if (send_lo < 0 || send_hi < 0 || send_lo > n || send_hi > n) { set_error("pdx_fem_explicit_step: bad send ranges"); return 1; }
     const int ns = pdx_model_num_states(model);
-    if (ns < 0 || (ns > 0 && (!states || !params))) { set_error("pdx_fem_explicit_step: bad model/states"); return 1; }
+    if (ns < 0 || ns > PDX_MAX_STATES || (ns > 0 && (!states || !params))) {
+        set_error("pdx_fem_explicit_step: bad model/states (closed-form models only)");
+        return 1;
+    }
     ExplArgs a{};
-    a.n = n; a.rowptr = rowptr; a.col = col; a.kval = kval; a.mlinv = mlinv; a.Uin = U_in; a.Uout = U_out; a.I0 = I0;
+    a.n = n; a.row_lo = row_lo; a.rowptr = rowptr; a.col = col; a.kval = kval; a.mlinv = mlinv;
+    a.Uin = U_in; a.Uout = U_out; a.I0 = I0;
+    a.mirror_lo = send_lo > 0 ? mirror_lo : nullptr; a.mirror_hi = send_hi > 0 ? mirror_hi : nullptr;
+    a.send_lo = send_lo; a.send_hi = send_hi;
     for (int i = 0; i < ns; ++i) a.st[i] = states[i];
     if (ns > 0) fill_model_params(model, params, dt, &a.mp); else a.mp.dt = dt;
-    constexpr int G = 8;
+    // lanes per row from the mean row length (P1 triangles ~7, tetrahedra ~15 entries per row)
+    int G = 8;
+    {
+        static thread_local const int32_t* cached_rp = nullptr;
+        static thread_local int cached_G = 8;
+        if (cached_rp != rowptr) {
+            int32_t last = 0;
+            if (cudaMemcpy(&last, rowptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                cached_G = pick_group(n, last);
+                cached_rp = rowptr;
+            }
+        }
+        G = cached_G;
+    }
     long long nb = ((long long)n * G + 255) / 256;
     if (nb > 148LL * 32) nb = 148LL * 32;
     cudaStream_t s = (cudaStream_t)stream;
@@ -383,6 +418,21 @@ int pdx_fem_explicit_step(int model, int math_mode, const float* params, int32_t
     }
     set_error("pdx_fem_explicit_step: unknown model");
     return 1;
+}
+
+int pdx_fem_explicit_step(int model, int math_mode, const float* params, int32_t n, const int32_t* rowptr,
+                          const int32_t* col, const float* kval, const float* mlinv, const float* U_in, float* U_out,
+                          float* const* states, const float* I0, float dt, void* stream) {
+    return explicit_step_impl(model, math_mode, params, n, 0, rowptr, col, kval, mlinv, U_in, U_out, states, I0, dt, 0,
+                              nullptr, 0, nullptr, stream);
+}
+
+int pdx_fem_explicit_step_part(int model, int math_mode, const float* params, int32_t n_local, int32_t row_lo,
+                               const int32_t* rowptr, const int32_t* col, const float* kval, const float* mlinv,
+                               const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
+                               int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream) {
+    return explicit_step_impl(model, math_mode, params, n_local, row_lo, rowptr, col, kval, mlinv, U_in, U_out, states,
+                              I0, dt, send_lo, mirror_lo, send_hi, mirror_hi, stream);
 }
 
 }  // extern "C"

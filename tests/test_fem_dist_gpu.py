@@ -1,0 +1,100 @@
+"""Row-block partitioned explicit lumped FEM step (config 5 path): one rank against the oracle,
+two/three ranks (NVLink symmetric memory, ghost stores fused into the step kernel) bitwise against one rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DIMS, H, SIGMA, DT = (13, 6, 8), (0.25, 0.25, 0.25), 1e-3, 0.1
+
+
+def _initial(n, dims):
+    U = np.full(n, -80.0, dtype=np.float32)
+    U[: 2 * dims[1] * dims[2]] = 20.0              # S1: the first two node planes
+    return U
+
+
+def test_single_rank_matches_oracle(cuda):
+    from oracle import fem as ofem
+    from oracle import ionic as oi
+    from pdensorflow_b200.fem_dist import PartitionedExplicitFEM
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    nx, ny, nz = DIMS
+    n = nx * ny * nz
+    rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA)
+    for math, tol in (('exact', 1e-6), ('fast', 1e-5)):
+        fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math=math)
+        U0 = _initial(n, DIMS)
+        fem.set_global_U(U0)
+        fem.step(50)
+        mo = oi.Fenton4v()
+        mo._dt = DT
+        mo.initialize_state_variables(U0[:, None])
+        mlinv = (1.0 / ml.astype(np.float64)).astype(np.float32)
+        Uo = U0.copy()
+        for _ in range(50):
+            Uo = ofem.explicit_lumped_step(mo, rp, ci, kv, mlinv, Uo, None, DT)
+        got = fem.current_U().cpu().numpy()
+        assert np.isfinite(got).all() and got.max() > 0.0
+        assert rel_l2(got, Uo) <= tol, (math, rel_l2(got, Uo))
+
+
+def _worker(rank, world, port, nsteps, q):
+    import torch.distributed as dist
+    from pdensorflow_b200.fem_dist import PartitionedExplicitFEM, row_blocks
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        nx, ny, nz = DIMS
+        n = nx * ny * nz
+        lo, hi = row_blocks(n, world)[rank]
+        rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA, lo, hi)
+        fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=rank, world=world)
+        assert (fem.send_lo > 0) == (rank > 0) and (fem.send_hi > 0) == (rank < world - 1)
+        fem.set_global_U(_initial(n, DIMS))
+        fem.step(nsteps)
+        torch.cuda.synchronize()
+        q.put((rank, lo, fem.owned_U().cpu().numpy(), fem.states[0].cpu().numpy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_partitioned_ranks_match_single_rank_bitwise(cuda, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
+    from pdensorflow_b200.fem_dist import PartitionedExplicitFEM
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    nsteps = 40
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    nx, ny, nz = DIMS
+    n = nx * ny * nz
+    rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA)
+    ref = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact')
+    ref.set_global_U(_initial(n, DIMS))
+    ref.step(nsteps)
+    Uref, Vref = ref.current_U().cpu().numpy(), ref.states[0].cpu().numpy()
+    for rank, lo, U, V in got:
+        assert np.array_equal(U, Uref[lo:lo + U.shape[0]])
+        assert np.array_equal(V, Vref[lo:lo + V.shape[0]])

@@ -1,0 +1,67 @@
+"""Host logic of the row-block partitioned FEM path (no GPU): the stencil-based generator of the
+structured tetrahedral operator against the general element-by-element assembly (oracle, which is
+itself pinned to the reference's NumPy assembly), the balanced row split, and the ghost-exchange plan."""
+import numpy as np
+import pytest
+
+from oracle import fem as ofem
+from pdensorflow_b200.fem_dist import plan_exchange, row_blocks
+from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator, tetrahedral_box
+
+
+@pytest.mark.parametrize('dims,h,sigma', [((5, 4, 6), (0.5, 0.25, 1.0), 0.7), ((3, 3, 3), (1.0, 1.0, 1.0), 1.0),
+                                          ((2, 7, 4), (0.1, 0.2, 0.3), 1e-3)])
+def test_structured_operator_equals_assembled_matrices(dims, h, sigma):
+    nx, ny, nz = dims
+    P, E, F = tetrahedral_box(nx, ny, nz, Lx=(nx - 1) * h[0], Ly=(ny - 1) * h[1], Lz=(nz - 1) * h[2])
+    m = ofem.assemble(P, E, F, {1: sigma}, {1: sigma})
+    rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, h, sigma)
+    assert np.array_equal(rp, m['rowptr']) and np.array_equal(ci, m['col'])      # same pattern, structural zeros included
+    np.testing.assert_allclose(kv, m['stiffness'], rtol=0, atol=2e-6 * np.abs(m['stiffness']).max())
+    n = nx * ny * nz
+    mass_rowsum = np.add.reduceat(m['mass'].astype(np.float64), m['rowptr'][:-1])
+    np.testing.assert_allclose(ml, mass_rowsum, rtol=1e-6)
+    np.testing.assert_allclose(ml.sum(dtype=np.float64), np.prod([(d - 1) * s for d, s in zip(dims, h)]), rtol=1e-6)
+    # K annihilates constants
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    assert np.abs(np.bincount(rows, weights=kv, minlength=n)).max() < 1e-5 * np.abs(kv).max()
+    # a row block is a slice of the full operator
+    lo, hi = n // 3, 2 * n // 3 + 1
+    rp2, ci2, kv2, ml2 = structured_tet_operator(nx, ny, nz, h, sigma, lo, hi)
+    assert np.array_equal(ci2, ci[rp[lo]:rp[hi]]) and np.array_equal(kv2, kv[rp[lo]:rp[hi]])
+    assert np.array_equal(rp2, rp[lo:hi + 1] - rp[lo]) and np.array_equal(ml2, ml[lo:hi])
+
+
+def test_row_blocks_are_balanced_and_cover():
+    for n, w in ((10, 3), (63001, 8), (7, 7), (20123648, 8)):
+        b = row_blocks(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_exchange_plan_on_a_banded_operator():
+    nx, ny, nz, world = 9, 4, 5, 3
+    n = nx * ny * nz
+    blocks = row_blocks(n, world)
+    ranges = []
+    for lo, hi in blocks:
+        _, ci, _, _ = structured_tet_operator(nx, ny, nz, row_lo=lo, row_hi=hi)
+        ranges.append((int(ci.min()), int(ci.max())))
+    band = ny * nz + nz + 1
+    for r in range(world):
+        send_lo, send_hi = plan_exchange(blocks, ranges, r)
+        assert (0 < send_lo <= band if r > 0 else send_lo == 0) and (0 < send_hi <= band if r < world - 1 else send_hi == 0)
+    # every ghost column of every rank is covered by what its neighbours send
+    for r, (lo, hi) in enumerate(blocks):
+        _, ci, _, _ = structured_tet_operator(nx, ny, nz, row_lo=lo, row_hi=hi)
+        ghosts = np.unique(ci[(ci < lo) | (ci >= hi)])
+        for g in ghosts:
+            owner = next(k for k, (a, b) in enumerate(blocks) if a <= g < b)
+            assert abs(owner - r) == 1
+            s_lo, s_hi = plan_exchange(blocks, ranges, owner)
+            a, b = blocks[owner]
+            assert (g < a + s_lo) if owner > r else (g >= b - s_hi)
+    with pytest.raises(ValueError):                       # ghosts two blocks away: not banded enough
+        plan_exchange(row_blocks(n, 9), [(max(lo - 3 * band, 0), min(hi + 3 * band, n) - 1) for lo, hi in row_blocks(n, 9)], 4)
