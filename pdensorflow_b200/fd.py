@@ -338,10 +338,12 @@ class DistributedFDStepper:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-        shape = (self.part.nx_array, global_shape[1], global_shape[2])
-        bufs = [symm.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
-        self._hdl = [symm.rendezvous(b, self.group if self.group is not None else dist.group.WORLD) for b in bufs]
-        return bufs
+        # symmetric allocations must have the same size on every rank: size them for the largest slab
+        nmax = -(-global_shape[0] // self.part.world) + 2
+        full = [symm.empty((nmax, global_shape[1], global_shape[2]), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._hdl = [symm.rendezvous(b, self.group if self.group is not None else dist.group.WORLD) for b in full]
+        self._symm_full = full
+        return [b[:self.part.nx_array] for b in full]
 
     def set_global(self, U, states=None, DIFF=None):
         """Install this rank's slab of global NumPy fields (ghost planes included)."""

@@ -51,10 +51,15 @@ def test_multi_gpu_slabs_match_single_gpu(cuda, halo, overlap, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, shape, nsteps, overlap, halo, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        got = [q.get(timeout=90) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                 # never leave a rank behind on the GPU
+            if p.is_alive():
+                p.kill()
     rng = np.random.default_rng(0)
     G = rng.uniform(-85, 25, size=shape).astype(np.float32)
     S = [rng.uniform(0, 1, size=shape).astype(np.float32) for _ in range(3)]

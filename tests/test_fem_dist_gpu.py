@@ -84,10 +84,15 @@ def test_partitioned_ranks_match_single_rank_bitwise(cuda, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, nsteps, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        got = [q.get(timeout=90) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                 # never leave a rank behind on the GPU
+            if p.is_alive():
+                p.kill()
     nx, ny, nz = DIMS
     n = nx * ny * nz
     rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA)
