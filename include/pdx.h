@@ -255,6 +255,16 @@ int pdx_fem_explicit_step_part(int model, int math_mode, const float* params, in
                                const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
                                int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream);
 
+/* The same partitioned step on a SELL-32 matrix (sliced ELLPACK, slice height 32 = one warp, one
+ * thread per row): slice_ptr int32 [ceil(n_local/32) + 1] gives each slice's offset into col / kval,
+ * entry k of row 32s + l sits at slice_ptr[s] + 32k + l, short rows are padded with (col = any valid
+ * global index, val = 0).  Every matrix access is a coalesced 128-byte warp load and every lane runs
+ * the ionic update; this is the layout pdensorflow_b200.fem_dist uses for config 5. */
+int pdx_fem_explicit_step_sell(int model, int math_mode, const float* params, int32_t n_local, int32_t row_lo,
+                               const int32_t* slice_ptr, const int32_t* col, const float* kval, const float* mlinv,
+                               const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
+                               int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream);
+
 /* ------------------------------------------------------------------ misc */
 int         pdx_version(void);
 const char* pdx_last_error(void);

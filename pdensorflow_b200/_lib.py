@@ -83,6 +83,8 @@ _SIGNATURES = {
                                         C.POINTER(_P), _P, C.c_float, _P]),
     'pdx_fem_explicit_step_part': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
                                              _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
+    'pdx_fem_explicit_step_sell': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
+                                             _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -251,6 +251,48 @@ __global__ void __launch_bounds__(256) fem_explicit_kernel(const __grid_constant
     }
 }
 
+// SELL-32 (sliced ELLPACK, slice height = warp size) form of the same step: ONE THREAD PER ROW.
+// Slice s holds rows 32s..32s+31 column-major: entry k of lane l at slice_ptr[s] + 32k + l, rows padded
+// to the slice's longest row with (col = own row, val = 0).  Every col/val load is a fully coalesced
+// 128-byte warp access, each thread keeps a whole row of gathers in flight, and - unlike the
+// lanes-per-row CSR kernel, where one lane in G does the ionic update - all 32 lanes run the ionic
+// model.  Products are accumulated in row order (k = 0, 1, ...).
+template <int MODEL, int MATH>
+__global__ void __launch_bounds__(256) fem_explicit_sell_kernel(const __grid_constant__ ExplArgs a) {
+    constexpr int NS = NStates<MODEL>::value;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slice = row >> 5, lane = threadIdx.x & 31;
+    if (slice * 32 >= a.n) return;                       // whole warp out of range
+    const int beg = a.rowptr[slice], end = a.rowptr[slice + 1];     // rowptr = slice_ptr here
+    const int32_t* __restrict__ col = a.col;
+    const float* __restrict__ val = a.kval;
+    float ku = 0.0f;
+#pragma unroll 4
+    for (int k = beg + lane; k < end; k += 32) ku = fmaf(val[k], a.Uin[col[k]], ku);
+    if (row >= a.n) return;
+    const size_t grow = (size_t)a.row_lo + row;
+    const float U = a.Uin[grow];
+    float st[PDX_MAX_STATES];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) st[s] = a.st[s][row];
+    float dU = MODEL != PDX_MODEL_NONE ? ionic_update<MODEL, MATH>(U, st, a.mp) : 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a.st[s][row] = st[s];
+    if (a.I0) dU += a.I0[row];
+    const float u1 = fmaf(-a.mp.dt * a.mlinv[row], ku, fmaf(a.mp.dt, dU, U));
+    a.Uout[grow] = u1;
+    if (a.mirror_lo && row < a.send_lo) a.mirror_lo[grow] = u1;
+    if (a.mirror_hi && row >= a.n - a.send_hi) a.mirror_hi[grow] = u1;
+}
+
+template <int MODEL, int MATH>
+int launch_expl_sell(const ExplArgs& a, cudaStream_t s) {
+    const unsigned nb = (unsigned)((a.n + 255) / 256);
+    fem_explicit_sell_kernel<MODEL, MATH><<<nb, 256, 0, s>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "fem_explicit_sell_kernel launch");
+}
+
 template <int MODEL, int MATH>
 int launch_expl(int G, const ExplArgs& a, unsigned nb, cudaStream_t s) {
     switch (G) {
@@ -368,7 +410,7 @@ int pdx_pcg_solve(pdx_pcg* s, const float* b, float* x, int maxiter, double toll
                       "pcg_kernel cooperative launch");
 }
 
-static int explicit_step_impl(int model, int math_mode, const float* params, int32_t n, int32_t row_lo,
+static int explicit_step_impl(bool sell, int model, int math_mode, const float* params, int32_t n, int32_t row_lo,
                               const int32_t* rowptr, const int32_t* col, const float* kval, const float* mlinv,
                               const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
                               int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream) {
@@ -389,6 +431,21 @@ static int explicit_step_impl(int model, int math_mode, const float* params, int
     a.send_lo = send_lo; a.send_hi = send_hi;
     for (int i = 0; i < ns; ++i) a.st[i] = states[i];
     if (ns > 0) fill_model_params(model, params, dt, &a.mp); else a.mp.dt = dt;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool ex = math_mode == PDX_MATH_EXACT;
+    if (sell) {
+        switch (model) {
+            case PDX_MODEL_NONE:     return launch_expl_sell<PDX_MODEL_NONE, PDX_MATH_FAST>(a, s);
+            case PDX_MODEL_FENTON4V: return ex ? launch_expl_sell<PDX_MODEL_FENTON4V, PDX_MATH_EXACT>(a, s)
+                                               : launch_expl_sell<PDX_MODEL_FENTON4V, PDX_MATH_FAST>(a, s);
+            case PDX_MODEL_MMS2V:    return ex ? launch_expl_sell<PDX_MODEL_MMS2V, PDX_MATH_EXACT>(a, s)
+                                               : launch_expl_sell<PDX_MODEL_MMS2V, PDX_MATH_FAST>(a, s);
+            case PDX_MODEL_MS2V:     return ex ? launch_expl_sell<PDX_MODEL_MS2V, PDX_MATH_EXACT>(a, s)
+                                               : launch_expl_sell<PDX_MODEL_MS2V, PDX_MATH_FAST>(a, s);
+        }
+        set_error("pdx_fem_explicit_step_sell: unknown model");
+        return 1;
+    }
     // lanes per row from the mean row length (P1 triangles ~7, tetrahedra ~15 entries per row)
     int G = 8;
     {
@@ -405,8 +462,6 @@ static int explicit_step_impl(int model, int math_mode, const float* params, int
     }
     long long nb = ((long long)n * G + 255) / 256;
     if (nb > 148LL * 32) nb = 148LL * 32;
-    cudaStream_t s = (cudaStream_t)stream;
-    const bool ex = math_mode == PDX_MATH_EXACT;
     switch (model) {
         case PDX_MODEL_NONE:     return launch_expl<PDX_MODEL_NONE, PDX_MATH_FAST>(G, a, (unsigned)nb, s);
         case PDX_MODEL_FENTON4V: return ex ? launch_expl<PDX_MODEL_FENTON4V, PDX_MATH_EXACT>(G, a, (unsigned)nb, s)
@@ -423,16 +478,24 @@ static int explicit_step_impl(int model, int math_mode, const float* params, int
 int pdx_fem_explicit_step(int model, int math_mode, const float* params, int32_t n, const int32_t* rowptr,
                           const int32_t* col, const float* kval, const float* mlinv, const float* U_in, float* U_out,
                           float* const* states, const float* I0, float dt, void* stream) {
-    return explicit_step_impl(model, math_mode, params, n, 0, rowptr, col, kval, mlinv, U_in, U_out, states, I0, dt, 0,
-                              nullptr, 0, nullptr, stream);
+    return explicit_step_impl(false, model, math_mode, params, n, 0, rowptr, col, kval, mlinv, U_in, U_out, states, I0, dt,
+                              0, nullptr, 0, nullptr, stream);
 }
 
 int pdx_fem_explicit_step_part(int model, int math_mode, const float* params, int32_t n_local, int32_t row_lo,
                                const int32_t* rowptr, const int32_t* col, const float* kval, const float* mlinv,
                                const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
                                int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream) {
-    return explicit_step_impl(model, math_mode, params, n_local, row_lo, rowptr, col, kval, mlinv, U_in, U_out, states,
-                              I0, dt, send_lo, mirror_lo, send_hi, mirror_hi, stream);
+    return explicit_step_impl(false, model, math_mode, params, n_local, row_lo, rowptr, col, kval, mlinv, U_in, U_out,
+                              states, I0, dt, send_lo, mirror_lo, send_hi, mirror_hi, stream);
+}
+
+int pdx_fem_explicit_step_sell(int model, int math_mode, const float* params, int32_t n_local, int32_t row_lo,
+                               const int32_t* slice_ptr, const int32_t* col, const float* kval, const float* mlinv,
+                               const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
+                               int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream) {
+    return explicit_step_impl(true, model, math_mode, params, n_local, row_lo, slice_ptr, col, kval, mlinv, U_in, U_out,
+                              states, I0, dt, send_lo, mirror_lo, send_hi, mirror_hi, stream);
 }
 
 }  // extern "C"

@@ -54,6 +54,32 @@ def plan_exchange(blocks, col_ranges, rank):
     return send_lo, send_hi
 
 
+def csr_to_sell32(rowptr, col, val, row_lo=0):
+    """CSR (local rows, global columns) -> SELL-32: (slice_ptr int32, col int32, val fp32).  Rows of a
+    32-row slice are padded to the slice's longest row with (col = the row's own global index, val = 0)
+    and stored column-major inside the slice (include/pdx.h, pdx_fem_explicit_step_sell)."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    n = rowptr.shape[0] - 1
+    lens = np.diff(rowptr)
+    nsl = (n + 31) // 32
+    lens_p = np.zeros(nsl * 32, dtype=np.int64)
+    lens_p[:n] = lens
+    width = lens_p.reshape(nsl, 32).max(axis=1)
+    slice_ptr = np.zeros(nsl + 1, dtype=np.int64)
+    np.cumsum(width * 32, out=slice_ptr[1:])
+    if slice_ptr[-1] >= 2 ** 31:
+        raise ValueError('SELL storage exceeds int32 offsets: partition the matrix over more ranks')
+    own = np.minimum(np.arange(nsl * 32, dtype=np.int64), n - 1) + row_lo
+    scol = np.repeat(own.reshape(nsl, 32), width, axis=0).reshape(-1)      # [sum(width), 32] rows -> padded with own index
+    sval = np.zeros(scol.shape[0], dtype=np.float32)
+    rows = np.repeat(np.arange(n, dtype=np.int64), lens)
+    k = np.arange(rowptr[-1], dtype=np.int64) - rowptr[rows]              # position of each entry inside its row
+    dst = slice_ptr[rows // 32] + k * 32 + (rows % 32)
+    scol[dst] = np.asarray(col, dtype=np.int64)
+    sval[dst] = np.asarray(val, dtype=np.float32)
+    return slice_ptr.astype(np.int32), scol.astype(np.int32), sval
+
+
 class PartitionedExplicitFEM:
     """One rank's block of the explicit lumped monodomain step.
 
@@ -63,7 +89,7 @@ class PartitionedExplicitFEM:
     """
 
     def __init__(self, n_global, rowptr, col, kval, mlump, dt, model='fenton4v', params=None, rank=0, world=1,
-                 group=None, math='fast', device=None):
+                 group=None, math='fast', device=None, layout='sell'):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != 'cuda':
             raise L.PdxError('PartitionedExplicitFEM needs a CUDA device: there is no CPU path')
@@ -85,6 +111,14 @@ class PartitionedExplicitFEM:
             ranges = [tuple(int(v) for v in t.tolist()) for t in allr]
             self.send_lo, self.send_hi = plan_exchange(self.blocks, ranges, rank)
         dev = self.device
+        self.layout = layout
+        self.nnz = int(rowptr[-1])
+        if layout == 'sell':
+            sp, scol, sval = csr_to_sell32(rowptr, col, kval, self.lo)
+            self.padding = scol.shape[0] / max(self.nnz, 1)
+            rowptr, col, kval = sp, scol, sval
+        elif layout != 'csr':
+            raise ValueError("layout must be 'sell' or 'csr'")
         self.rowptr = torch.from_numpy(rowptr).to(dev)
         self.col = torch.from_numpy(col).to(dev)
         self.kval = torch.from_numpy(np.ascontiguousarray(kval, dtype=np.float32)).to(dev)
@@ -136,9 +170,10 @@ class PartitionedExplicitFEM:
             self._prime()
         lib = L.lib()
         dt32 = float(np.float32(self.dt))
+        fn = lib.pdx_fem_explicit_step_sell if self.layout == 'sell' else lib.pdx_fem_explicit_step_part
         for _ in range(nsteps):
             i, o = self._cur, self._cur ^ 1
-            L.check(lib.pdx_fem_explicit_step_part(
+            L.check(fn(
                 self.model_id, self.math_id, self._params, self.nloc, self.lo, L.ptr(self.rowptr), L.ptr(self.col),
                 L.ptr(self.kval), L.ptr(self.mlinv), L.ptr(self.U[i]), L.ptr(self.U[o]), self._states_arr, L.ptr(I0),
                 dt32, self.send_lo, C.c_void_p(self._peer_lo[o]), self.send_hi, C.c_void_p(self._peer_hi[o]),

@@ -28,8 +28,8 @@ def test_single_rank_matches_oracle(cuda):
     nx, ny, nz = DIMS
     n = nx * ny * nz
     rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA)
-    for math, tol in (('exact', 1e-6), ('fast', 1e-5)):
-        fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math=math)
+    for math, tol, layout in (('exact', 1e-6, 'sell'), ('fast', 1e-5, 'sell'), ('exact', 1e-6, 'csr'), ('fast', 1e-5, 'csr')):
+        fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math=math, layout=layout)
         U0 = _initial(n, DIMS)
         fem.set_global_U(U0)
         fem.step(50)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument('--n', type=int, default=272)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--skip-config1', action='store_true')
+    ap.add_argument('--layout', default='sell', choices=['sell', 'csr'])
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -35,7 +36,8 @@ def main():
     # h = 0.25 mm, sigma = 1e-3 (Tests/FEM/Fenton/fenton.py:64-65), dt = 0.1: dt*lambda_max ~ 0.5
     rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, (0.25, 0.25, 0.25), 1e-3, lo, hi)
     setup = time.time() - t0
-    fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, 0.1, model='fenton4v', math='fast', rank=rank, world=world)
+    fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, 0.1, model='fenton4v', math='fast', rank=rank, world=world,
+                                 layout=args.layout)
     U = fem.current_U()
     U.fill_(-80.0)
     U[: 2 * ny * nz] = 20.0
@@ -61,7 +63,8 @@ def main():
                           'n_gpus': world, 'ms_per_step': round(ms, 4), 'gnode_steps_per_s': round(n / ms / 1e6, 2),
                           'nnz_per_row': round(rbar, 2), 'algorithmic_bytes_per_node_step': round(bpn, 1),
                           'algorithmic_gbs_per_gpu': round(n / world * bpn / ms / 1e6, 1), 'setup_s_per_rank': round(setup, 1),
-                          'ghost_rows_sent': [fem.send_lo, fem.send_hi], 'finite': ok}), flush=True)
+                          'ghost_rows_sent': [fem.send_lo, fem.send_hi], 'finite': ok, 'layout': args.layout,
+                          'sell_padding': round(getattr(fem, 'padding', 1.0), 4)}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
