@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PDX_VERSION 110
+#define PDX_VERSION 120
 
 /* ionic models: gpuSolve/ionic/{fenton4v,mms2v,ms2v,courtemanche_ramirez_nattel,
  * ten_tusscher_panfilov}.py.  CRN and TTP are the lookup-table models (pdx_lut_model below). */
@@ -264,6 +264,57 @@ int pdx_fem_explicit_step_sell(int model, int math_mode, const float* params, in
                                const int32_t* slice_ptr, const int32_t* col, const float* kval, const float* mlinv,
                                const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
                                int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream);
+
+/* ------------------------------------------------------------------ FEM path across GPUs */
+/* Row-block partitioned Jacobi-PCG = the semi-implicit step of MonodomainSolver / HeatSolver
+ * (monodomainSolver.py:98-108, heatSolver.py:127-135, conjgrad.py:172-203,257-312) with the mesh nodes
+ * split into contiguous row blocks, one per GPU (the reference has no multi-GPU
+ * path).  One persistent cooperative kernel per rank per solve; the ranks communicate from inside the
+ * kernel through NVLink peer memory only (8-byte (epoch,value) words for the two dot products of an
+ * iteration, z = Minv*r of the edge rows for the ghosts) - see pdx_fem_part.cu.
+ *
+ * Vectors multiplied by the matrix are WINDOWS of ghost_lo + n_local + ghost_hi floats: the ghost_lo
+ * rows owned by rank-1 just below this rank's first row, the owned rows, the ghost_hi rows of rank+1
+ * just above.  col[] holds window-local indices.  send_lo / send_hi = how many of this rank's first /
+ * last rows the lower / upper neighbour holds as ghosts (= that neighbour's ghost_hi / ghost_lo);
+ * lower_window_index = the index of this rank's row 0 in the lower neighbour's window
+ * (its ghost_lo + n_local), upper_window_index = the index of this rank's row n_local - send_hi in the
+ * upper neighbour's window (its ghost_lo - send_hi).
+ *
+ * Workspace: every rank allocates pdx_pcg_part_workspace_bytes(max_window) bytes (max_window = the
+ * largest window over the ranks, so that the layout is the same everywhere) of peer-accessible device
+ * memory (symmetric memory / CUDA IPC / plain device memory for ranks that share a GPU) and passes all
+ * `world` base pointers, as mapped in THIS process, to create.  The x window (potential: guess on
+ * entry, solution on exit, ghosts kept consistent by the kernel) and the rhs0 window live inside it.
+ * All ranks must have returned from create before any rank calls solve (create clears the block). */
+#define PDX_PART_MAX_WORLD 16
+typedef struct pdx_pcg_part_desc {
+    int32_t n_local, ghost_lo, ghost_hi;
+    int32_t rank, world;
+    int32_t send_lo, send_hi;
+    int32_t lower_window_index, upper_window_index;
+    int32_t max_blocks;          /* cap on the cooperative grid (0 = auto); ranks sharing one GPU must fit together */
+    int32_t timeout_ms;          /* a rank waiting longer than this for a peer gives up (0 = 10000) */
+    const int32_t* rowptr;       /* n_local + 1 */
+    const int32_t* col;          /* window-local */
+    const float*   aval;         /* A = MASS + dt*STIFFNESS, rows of this rank */
+    const float*   mval;         /* MASS on the same pattern, or NULL */
+    const float*   minv;         /* 1/diag(A) of the owned rows, or NULL */
+} pdx_pcg_part_desc;
+typedef struct pdx_pcg_part pdx_pcg_part;
+int64_t pdx_pcg_part_workspace_bytes(int32_t max_window);
+int     pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_workspaces /* world */,
+                            int32_t max_window, pdx_pcg_part** out);
+void    pdx_pcg_part_destroy(pdx_pcg_part* s);
+float*  pdx_pcg_part_x(pdx_pcg_part* s);        /* window, device */
+float*  pdx_pcg_part_rhs0(pdx_pcg_part* s);     /* window, device */
+int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s);
+/* Solve A x = b on the x window.  b: n_local values, or NULL to use b = MASS * rhs0 with the rhs0
+ * window (all of it, ghosts included, valid on entry: fem_dist runs the ionic update over the window).
+ * Every rank must call it with the same maxiter / toll / check_every.  info as pdx_pcg_solve, plus
+ * flag bit2 = a peer did not answer within timeout_ms (fatal for the handle). */
+int     pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, int maxiter, double toll, int check_every,
+                           int32_t* info /* device, 4 words */, void* stream);
 
 /* ------------------------------------------------------------------ misc */
 int         pdx_version(void);

@@ -47,6 +47,17 @@ class LutModel(C.Structure):
                 ('consts', C.c_float * LUT_MAX_CONSTS)]
 
 
+class PcgPartDesc(C.Structure):
+    """struct pdx_pcg_part_desc (include/pdx.h)."""
+    _fields_ = [('n_local', C.c_int32), ('ghost_lo', C.c_int32), ('ghost_hi', C.c_int32),
+                ('rank', C.c_int32), ('world', C.c_int32), ('send_lo', C.c_int32), ('send_hi', C.c_int32),
+                ('lower_window_index', C.c_int32), ('upper_window_index', C.c_int32),
+                ('max_blocks', C.c_int32), ('timeout_ms', C.c_int32),
+                ('rowptr', C.c_void_p), ('col', C.c_void_p), ('aval', C.c_void_p), ('mval', C.c_void_p),
+                ('minv', C.c_void_p)]
+
+
+PART_MAX_WORLD = 16
 _lib = None
 
 _P = C.c_void_p
@@ -85,6 +96,13 @@ _SIGNATURES = {
                                              _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
     'pdx_fem_explicit_step_sell': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
                                              _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
+    'pdx_pcg_part_workspace_bytes': (C.c_int64, [C.c_int32]),
+    'pdx_pcg_part_create': (C.c_int, [C.POINTER(PcgPartDesc), C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
+    'pdx_pcg_part_destroy': (None, [_P]),
+    'pdx_pcg_part_x': (_P, [_P]),
+    'pdx_pcg_part_rhs0': (_P, [_P]),
+    'pdx_pcg_part_blocks': (C.c_int32, [_P]),
+    'pdx_pcg_part_solve': (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -7,6 +7,7 @@
 #include <cooperative_groups.h>
 #include <new>
 #include "pdx_internal.h"
+#include "pdx_fem_dev.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -14,20 +15,6 @@ namespace pdx {
 namespace {
 
 // ---------------------------------------------------------------- SpMV
-// G lanes cooperate on one row (G chosen from the mean row length).
-template <int G>
-__device__ __forceinline__ float row_dot(const int32_t* __restrict__ col, const float* __restrict__ val,
-                                         const float* x, int beg, int end, int sub, bool cg_loads) {
-    float acc = 0.0f;
-    for (int k = beg + sub; k < end; k += G) {
-        const float xv = cg_loads ? __ldcg(x + col[k]) : x[col[k]];
-        acc = fmaf(val[k], xv, acc);
-    }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
-    return acc;
-}
-
 template <int G>
 __global__ void __launch_bounds__(256) spmv_kernel(int n, const int32_t* __restrict__ rowptr,
                                                    const int32_t* __restrict__ col, const float* __restrict__ val,
@@ -41,14 +28,6 @@ __global__ void __launch_bounds__(256) spmv_kernel(int n, const int32_t* __restr
         const float acc = row_dot<G>(col, val, x, valid ? rowptr[row] : 0, valid ? rowptr[row + 1] : 0, sub, false);
         if (valid && sub == 0) y[row] = acc;
     }
-}
-
-int pick_group(int n, int64_t nnz) {
-    const double mean = n > 0 ? (double)nnz / n : 1.0;
-    if (mean <= 6) return 4;
-    if (mean <= 12) return 8;
-    if (mean <= 24) return 16;
-    return 32;
 }
 
 // ---------------------------------------------------------------- PCG (cooperative)
@@ -67,32 +46,6 @@ struct PcgArgs {
     double toll_sq;
     int32_t* info;
 };
-
-__device__ __forceinline__ float block_sum(float v, float* sh) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) sh[w] = v;
-    __syncthreads();
-    float t = 0.0f;
-    const int nw = blockDim.x >> 5;
-    if (w == 0) {
-        t = lane < nw ? sh[lane] : 0.0f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) sh[32] = t;
-    }
-    __syncthreads();
-    return sh[32];
-}
-
-// Sum of the per-block partials, same order in every block => every block gets the same bits.
-__device__ __forceinline__ float grid_total(const float* part, float* sh) {
-    float v = 0.0f;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(part + i);
-    return block_sum(v, sh);
-}
 
 template <int G>
 __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArgs a) {

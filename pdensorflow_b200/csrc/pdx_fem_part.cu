@@ -1,0 +1,428 @@
+// pdx_fem_part.cu - row-block partitioned Jacobi-PCG: the semi-implicit FEM step across GPUs
+// (FEM: "per SpMV one ghost exchange, per CG iteration two scalar all-reduces").
+//
+// Same mathematics as pcg_kernel (pdx_fem.cu; reference linearsolvers/conjgrad.py:172-203,257-312,
+// jacobi_precond.py:35-41), one PERSISTENT COOPERATIVE KERNEL PER RANK per solve.  The ranks talk only
+// through NVLink peer memory, from inside the kernel:
+//
+//  * Every rank owns n rows and keeps WINDOWS [ghost_lo | n | ghost_hi] of the vectors the matrix
+//    multiplies (x, p, rhs0); column indices are window-local.  The matrix must be banded enough for the
+//    ghosts to be the neighbours' edge rows (RCM / structured order, fem_dist.plan_windows checks it).
+//  * Ghost values are never "exchanged" as such.  x and p ghosts are RECOMPUTED locally with the same
+//    arithmetic the owner uses (x_g = fma(alpha, p_g, x_g); p_g = fma(beta, p_g, z_g)), which needs only
+//    z = Minv*r of the neighbours' edge rows.  Those are stored by the owner straight into this rank's
+//    ghost slots while it updates r, and they become visible with the all-reduce that follows anyway.
+//  * The two dot products of an iteration are all-reduced through peer memory: block 0 publishes the
+//    rank total into slot[rank] of EVERY rank as one 8-byte (epoch, value) word with release semantics,
+//    then waits for the `world` words in its own slots, adds them in rank order (same bits on every
+//    rank, so every rank takes the same convergence decision) and hands the result to the other blocks.
+//    The release/acquire pair on the slot also orders the z stores of the same phase.
+//  * So an iteration costs 2 exchanges of 8 bytes per peer and nothing else; no NCCL call, no host
+//    involvement, no extra launch.  A rank that never shows up makes block 0 time out (timeout_ms) and
+//    the solve return flag bit 2 instead of hanging the GPU.
+#include <cooperative_groups.h>
+#include <new>
+#include "pdx_internal.h"
+#include "pdx_fem_dev.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pdx {
+namespace {
+
+constexpr int MAXW = PDX_PART_MAX_WORLD;
+
+// Communication block at the start of every rank's symmetric workspace.
+struct Comm {
+    unsigned long long slot[2][2][MAXW];   // [epoch parity][which scalar][source rank] = epoch << 32 | float bits
+    unsigned long long bcast[2];           // block 0 -> other blocks of this rank
+    unsigned int abort_flag;
+    unsigned int epoch;                    // all-reduces completed so far (identical on every rank)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long pack(unsigned int epoch, float v) {
+    return ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+}
+
+struct PartArgs {
+    int n, glo, ghi;                 // owned rows, ghost rows below / above
+    const int32_t* rowptr;
+    const int32_t* col;              // window-local
+    const float* aval;               // A = M + dt K
+    const float* mval;               // optional: b = M * rhs0 (same pattern)
+    const float* minv;               // n, may be null
+    const float* b;                  // n (used when mval == null)
+    const float* rhs0;               // window (used when mval != null)
+    float* x;                        // window
+    float* p;                        // window
+    float* zg;                       // window; only the ghost parts are used
+    float *r, *q;                    // n
+    float* part;                     // 2 * gridDim.x
+    Comm* comm;
+    Comm* peer[MAXW];
+    // where this rank's first send_lo / last send_hi rows live in the neighbours' windows
+    float* peer_lo_p;  float* peer_lo_zg;     // indexed by own row i            (i < send_lo)
+    float* peer_hi_p;  float* peer_hi_zg;     // indexed by i - (n - send_hi)    (i >= n - send_hi)
+    int send_lo, send_hi;
+    int rank, world;
+    int maxiter, check_every;
+    double toll_sq;
+    unsigned long long timeout_ns;
+    int32_t* info;
+};
+
+// All-reduce of NV (1 or 2) scalars over the ranks.  Returns false when a peer timed out.
+// Every thread of the grid calls it; loc[] are the thread's partial sums.
+template <int NV>
+__device__ __forceinline__ bool all_reduce(const PartArgs& a, cg::grid_group& grid, unsigned int& epoch, float* sh,
+                                           float loc0, float loc1, float* out0, float* out1) {
+    const int nb = gridDim.x;
+    float v0 = block_sum(loc0, sh);
+    float v1 = NV > 1 ? block_sum(loc1, sh) : 0.0f;
+    if (threadIdx.x == 0) {
+        __stcg(a.part + blockIdx.x, v0);
+        if (NV > 1) __stcg(a.part + nb + blockIdx.x, v1);
+    }
+    __threadfence_system();          // this thread's peer stores (z of the edge rows) before the publication
+    grid.sync();
+    ++epoch;
+    const int par = epoch & 1;
+    Comm* me = a.comm;
+    if (blockIdx.x == 0) {
+        const float t0 = grid_total(a.part, sh);
+        const float t1 = NV > 1 ? grid_total(a.part + nb, sh) : 0.0f;
+        __shared__ float got[2][MAXW];
+        __shared__ int timed_out;
+        if (threadIdx.x == 0) timed_out = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < a.world) {
+            const int peer = threadIdx.x;
+            __threadfence_system();
+            st_release_sys(&a.peer[peer]->slot[par][0][a.rank], pack(epoch, t0));
+            if (NV > 1) st_release_sys(&a.peer[peer]->slot[par][1][a.rank], pack(epoch, t1));
+            const unsigned long long t_start = global_ns();
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                unsigned long long w;
+                unsigned int spins = 0;
+                while ((unsigned int)((w = ld_acquire_sys(&me->slot[par][v][peer])) >> 32) != epoch) {
+                    if ((++spins & 1023u) == 0 && global_ns() - t_start > a.timeout_ns) { timed_out = 1; break; }
+                }
+                got[v][peer] = __uint_as_float((unsigned int)w);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s0 = 0.0f, s1 = 0.0f;
+            for (int rk = 0; rk < a.world; ++rk) { s0 += got[0][rk]; if (NV > 1) s1 += got[1][rk]; }
+            if (timed_out) { me->abort_flag = 1u; __threadfence(); }
+            if (NV > 1) st_release_gpu(&me->bcast[1], pack(epoch, s1));
+            st_release_gpu(&me->bcast[0], pack(epoch, s0));
+        }
+    }
+    __shared__ unsigned long long res[2];
+    __shared__ unsigned int aborted;
+    if (threadIdx.x == 0) {
+        unsigned long long w;
+        while ((unsigned int)((w = ld_acquire_gpu(&me->bcast[0])) >> 32) != epoch) { }
+        res[0] = w;
+        if (NV > 1) res[1] = ld_acquire_gpu(&me->bcast[1]);   // written before bcast[0]
+        aborted = *((volatile unsigned int*)&me->abort_flag);
+    }
+    __syncthreads();
+    *out0 = __uint_as_float((unsigned int)res[0]);
+    if (NV > 1) *out1 = __uint_as_float((unsigned int)res[1]);
+    const bool ok = aborted == 0u;
+    __syncthreads();                 // res[] is reused by the next call
+    return ok;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) pcg_part_kernel(const __grid_constant__ PartArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float sh[33];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const int gid = tid / G, sub = threadIdx.x % G, ngroups = nthreads / G;
+    const int nround = (a.n + ngroups - 1) / ngroups * ngroups;
+    const int glo = a.glo;
+    const int hi_first = a.n - a.send_hi;          // first row the upper neighbour holds as a ghost
+    unsigned int epoch = *((volatile unsigned int*)&a.comm->epoch);
+
+    // b = M rhs0 (optional) ; r = b - A x ; z = Minv r ; p = z ; rz = r.z      (conjgrad.py:191-203)
+    float loc_rz = 0.0f, loc_rr = 0.0f;
+    for (int row = gid; row < nround; row += ngroups) {
+        const bool valid = row < a.n;
+        const int beg = valid ? a.rowptr[row] : 0, end = valid ? a.rowptr[row + 1] : 0;
+        const float ax = row_dot<G>(a.col, a.aval, a.x, beg, end, sub, true);
+        float bv = 0.0f;
+        if (a.mval) bv = row_dot<G>(a.col, a.mval, a.rhs0, beg, end, sub, true);   // uniform branch
+        if (valid && sub == 0) {
+            if (!a.mval) bv = a.b[row];
+            const float r = __fsub_rn(bv, ax);
+            const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
+            __stcg(a.r + row, r);
+            __stcg(a.p + glo + row, z);
+            if (row < a.send_lo) a.peer_lo_p[row] = z;                 // the neighbours' ghost p = z
+            if (row >= hi_first) a.peer_hi_p[row - hi_first] = z;
+            loc_rz = fmaf(r, z, loc_rz);
+            loc_rr = fmaf(r, r, loc_rr);
+        }
+    }
+    float rz, res;
+    bool ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rz, &res);
+
+    int niters = 0, flags = 0;
+    for (int k = 1; ok && k <= a.maxiter; ++k) {
+        niters = k;
+        // q = A p ; pq = p.q
+        float loc_pq = 0.0f;
+        for (int row = gid; row < nround; row += ngroups) {
+            const bool valid = row < a.n;
+            const float ap = row_dot<G>(a.col, a.aval, a.p, valid ? a.rowptr[row] : 0, valid ? a.rowptr[row + 1] : 0,
+                                        sub, true);
+            if (valid && sub == 0) {
+                __stcg(a.q + row, ap);
+                loc_pq = fmaf(__ldcg(a.p + glo + row), ap, loc_pq);
+            }
+        }
+        float pq, unused;
+        ok = all_reduce<1>(a, grid, epoch, sh, loc_pq, 0.0f, &pq, &unused);
+        if (!ok) break;
+        const float alpha = rz / pq;
+        // x += alpha p ; r -= alpha q ; res = r.r ; z = Minv r ; rz' = r.z        (conjgrad.py:172-183)
+        loc_rz = 0.0f; loc_rr = 0.0f;
+        for (int i = tid; i < a.n; i += nthreads) {
+            const float pi = __ldcg(a.p + glo + i);
+            __stcg(a.x + glo + i, fmaf(alpha, pi, __ldcg(a.x + glo + i)));
+            const float r = fmaf(-alpha, __ldcg(a.q + i), __ldcg(a.r + i));
+            __stcg(a.r + i, r);
+            const float z = a.minv ? __fmul_rn(a.minv[i], r) : r;
+            if (i < a.send_lo) a.peer_lo_zg[i] = z;                    // edge rows: z into the neighbours' ghost slots
+            if (i >= hi_first) a.peer_hi_zg[i - hi_first] = z;
+            loc_rr = fmaf(r, r, loc_rr);
+            loc_rz = fmaf(r, z, loc_rz);
+        }
+        // ghost x, recomputed exactly as its owner computes it
+        for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
+            const int w = g < a.glo ? g : a.n + g;
+            __stcg(a.x + w, fmaf(alpha, __ldcg(a.p + w), __ldcg(a.x + w)));
+        }
+        float rznew;
+        ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rznew, &res);
+        if (!ok) break;
+        // batched convergence test + NaN/Inf guard (conjgrad.py:293-300); p is not needed after the last iteration
+        if (k % a.check_every == 0) {
+            const bool finite = isfinite(res);
+            if (!finite || (double)res < a.toll_sq) {
+                if (!finite) flags |= 2;
+                break;
+            }
+        }
+        if (k == a.maxiter) break;
+        const float beta = rznew / rz;
+        // p = z + beta p, owned rows and ghosts alike
+        for (int i = tid; i < a.n; i += nthreads) {
+            const float r = __ldcg(a.r + i);
+            const float z = a.minv ? __fmul_rn(a.minv[i], r) : r;
+            __stcg(a.p + glo + i, fmaf(beta, __ldcg(a.p + glo + i), z));
+        }
+        for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
+            const int w = g < a.glo ? g : a.n + g;
+            __stcg(a.p + w, fmaf(beta, __ldcg(a.p + w), __ldcg(a.zg + w)));
+        }
+        rz = rznew;
+        grid.sync();
+    }
+    if (!ok) flags |= 4;
+    if (niters >= a.maxiter) flags |= 1;
+    if (tid == 0) {
+        a.comm->epoch = epoch;
+        if (a.info) {
+            a.info[0] = niters;
+            a.info[1] = __float_as_int(res);
+            a.info[2] = flags;
+            a.info[3] = 0;
+        }
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t COMM_BYTES = 4096;
+static_assert(sizeof(Comm) <= COMM_BYTES, "Comm must fit its slot of the workspace");
+
+}  // namespace
+}  // namespace pdx
+
+using namespace pdx;
+
+struct pdx_pcg_part {
+    pdx_pcg_part_desc d;
+    int window;
+    int64_t nnz;
+    int G, nblocks;
+    char* ws;               // own workspace
+    float *x, *p, *zg, *rhs0;
+    float* work;            // r, q
+    float* part;
+    PartArgs base;
+};
+
+extern "C" {
+
+int64_t pdx_pcg_part_workspace_bytes(int32_t max_window) {
+    if (max_window <= 0) return 0;
+    return (int64_t)(COMM_BYTES + 4 * align_up(sizeof(float) * (size_t)max_window, 256));
+}
+
+int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_t max_window, pdx_pcg_part** out) {
+    if (!d || !peer_ws || !out) { set_error("pdx_pcg_part_create: null argument"); return 1; }
+    if (d->n_local <= 0 || d->ghost_lo < 0 || d->ghost_hi < 0 || !d->rowptr || !d->col || !d->aval) {
+        set_error("pdx_pcg_part_create: bad matrix description");
+        return 1;
+    }
+    if (d->world < 1 || d->world > MAXW || d->rank < 0 || d->rank >= d->world) {
+        set_error("pdx_pcg_part_create: world must be 1.." + std::to_string(MAXW) + " and 0 <= rank < world");
+        return 1;
+    }
+    const int window = d->ghost_lo + d->n_local + d->ghost_hi;
+    if (window > max_window) { set_error("pdx_pcg_part_create: window exceeds max_window"); return 1; }
+    if (d->send_lo < 0 || d->send_hi < 0 || d->send_lo > d->n_local || d->send_hi > d->n_local ||
+        (d->rank == 0 && (d->send_lo || d->ghost_lo)) || (d->rank == d->world - 1 && (d->send_hi || d->ghost_hi))) {
+        set_error("pdx_pcg_part_create: bad ghost / send counts");
+        return 1;
+    }
+    if ((d->send_lo > 0 && d->lower_window_index < 0) || (d->send_hi > 0 && d->upper_window_index < 0)) {
+        set_error("pdx_pcg_part_create: neighbour window indices missing");
+        return 1;
+    }
+    for (int r = 0; r < d->world; ++r)
+        if (!peer_ws[r]) { set_error("pdx_pcg_part_create: null peer workspace"); return 1; }
+    pdx_pcg_part* s = new (std::nothrow) pdx_pcg_part();
+    if (!s) { set_error("out of memory"); return 1; }
+    s->d = *d;
+    s->window = window;
+    int32_t last = 0;
+    if (check_cuda(cudaMemcpy(&last, d->rowptr + d->n_local, sizeof(int32_t), cudaMemcpyDeviceToHost), "read nnz")) {
+        delete s; return 1;
+    }
+    s->nnz = last;
+    s->G = pick_group(d->n_local, s->nnz);
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e;
+    switch (s->G) {
+        case 4:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<4>, 256, 0); break;
+        case 8:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<8>, 256, 0); break;
+        case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<16>, 256, 0); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<32>, 256, 0); break;
+    }
+    if (check_cuda(e, "occupancy query") || per_sm < 1) {
+        if (per_sm < 1) set_error("pcg_part kernel cannot be resident");
+        delete s; return 1;
+    }
+    long long want = ((long long)d->n_local * s->G + 255) / 256;
+    long long cap = (long long)sms * (per_sm > 4 ? 4 : per_sm);
+    long long nb = want < cap ? want : cap;
+    if (nb > sms && (long long)d->n_local * s->G <= (long long)sms * 256 * 8) nb = sms;
+    if (d->max_blocks > 0 && nb > d->max_blocks) nb = d->max_blocks;
+    if (nb < 1) nb = 1;
+    s->nblocks = (int)nb;
+    const size_t vec = align_up(sizeof(float) * (size_t)max_window, 256);
+    s->ws = (char*)peer_ws[d->rank];
+    s->p    = (float*)(s->ws + COMM_BYTES);
+    s->zg   = (float*)(s->ws + COMM_BYTES + vec);
+    s->x    = (float*)(s->ws + COMM_BYTES + 2 * vec);
+    s->rhs0 = (float*)(s->ws + COMM_BYTES + 3 * vec);
+    if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 2 * (size_t)d->n_local), "cudaMalloc(pcg_part work)")) { delete s; return 1; }
+    if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 2 * (size_t)s->nblocks), "cudaMalloc(pcg_part partials)")) {
+        cudaFree(s->work); delete s; return 1;
+    }
+    if (check_cuda(cudaMemset(s->ws, 0, COMM_BYTES + 2 * vec), "clear comm block") ||     // comm, p, zg
+        check_cuda(cudaDeviceSynchronize(), "clear comm block (sync)")) {
+        cudaFree(s->work); cudaFree(s->part); delete s; return 1;
+    }
+    PartArgs& a = s->base;
+    a = PartArgs{};
+    a.n = d->n_local; a.glo = d->ghost_lo; a.ghi = d->ghost_hi;
+    a.rowptr = d->rowptr; a.col = d->col; a.aval = d->aval; a.mval = d->mval; a.minv = d->minv;
+    a.x = s->x; a.p = s->p; a.zg = s->zg; a.rhs0 = s->rhs0;
+    a.r = s->work; a.q = s->work + d->n_local;
+    a.part = s->part;
+    a.comm = (Comm*)s->ws;
+    for (int r = 0; r < d->world; ++r) a.peer[r] = (Comm*)peer_ws[r];
+    a.send_lo = d->send_lo; a.send_hi = d->send_hi;
+    if (d->send_lo > 0) {
+        char* w = (char*)peer_ws[d->rank - 1];
+        a.peer_lo_p  = (float*)(w + COMM_BYTES) + d->lower_window_index;
+        a.peer_lo_zg = (float*)(w + COMM_BYTES + vec) + d->lower_window_index;
+    }
+    if (d->send_hi > 0) {
+        char* w = (char*)peer_ws[d->rank + 1];
+        a.peer_hi_p  = (float*)(w + COMM_BYTES) + d->upper_window_index;
+        a.peer_hi_zg = (float*)(w + COMM_BYTES + vec) + d->upper_window_index;
+    }
+    a.rank = d->rank; a.world = d->world;
+    a.timeout_ns = (unsigned long long)(d->timeout_ms > 0 ? d->timeout_ms : 10000) * 1000000ull;
+    *out = s;
+    return 0;
+}
+
+void pdx_pcg_part_destroy(pdx_pcg_part* s) {
+    if (!s) return;
+    cudaFree(s->work);
+    cudaFree(s->part);
+    delete s;
+}
+
+float* pdx_pcg_part_x(pdx_pcg_part* s) { return s ? s->x : nullptr; }
+float* pdx_pcg_part_rhs0(pdx_pcg_part* s) { return s ? s->rhs0 : nullptr; }
+int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s) { return s ? s->nblocks : 0; }
+
+int pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, int maxiter, double toll, int check_every, int32_t* info,
+                       void* stream) {
+    if (!s || maxiter < 0) { set_error("pdx_pcg_part_solve: bad arguments"); return 1; }
+    if (!b && !s->d.mval) { set_error("pdx_pcg_part_solve: b is NULL and the handle has no mass matrix"); return 1; }
+    PartArgs a = s->base;
+    a.b = b;
+    if (b) a.mval = nullptr;
+    a.maxiter = maxiter;
+    a.check_every = check_every > 0 ? check_every : 1;
+    a.toll_sq = toll * toll;
+    a.info = info;
+    void* args[] = {&a};
+    const void* fn;
+    switch (s->G) {
+        case 4:  fn = (const void*)pcg_part_kernel<4>; break;
+        case 8:  fn = (const void*)pcg_part_kernel<8>; break;
+        case 16: fn = (const void*)pcg_part_kernel<16>; break;
+        default: fn = (const void*)pcg_part_kernel<32>; break;
+    }
+    count_launch();
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(s->nblocks), dim3(256), args, 0, (cudaStream_t)stream),
+                      "pcg_part_kernel cooperative launch");
+}
+
+}  // extern "C"

@@ -182,3 +182,226 @@ class PartitionedExplicitFEM:
                 self._hdl[0].barrier(channel=0)
             self._cur = o
         self.nsteps_done += nsteps
+
+
+# ------------------------------------------------------------------------------------------------
+# Semi-implicit step (MonodomainSolver.solve_step) across GPUs
+# ------------------------------------------------------------------------------------------------
+def plan_windows(blocks, col_ranges):
+    """Ghost windows of a row-block partition of a banded matrix.
+
+    blocks: [(lo, hi)] per rank; col_ranges: [(min_col, max_col)] of each rank's rows (global indices).
+    Returns one dict per rank: ghost_lo / ghost_hi (rows of the lower / upper neighbour this rank's rows
+    reach), send_lo / send_hi (how many of its first / last rows the neighbours hold as ghosts) and the
+    index of those rows in the neighbours' windows (include/pdx.h, pdx_pcg_part_desc).  Raises when a
+    rank's columns reach beyond its two neighbours (reorder the mesh: RCM)."""
+    world = len(blocks)
+    plans = []
+    for r, ((lo, hi), (cmin, cmax)) in enumerate(zip(blocks, col_ranges)):
+        lo_limit = blocks[r - 1][0] if r > 0 else lo
+        hi_limit = blocks[r + 1][1] if r < world - 1 else hi
+        if cmin < lo_limit or cmax >= hi_limit:
+            raise ValueError('rank %d needs columns [%d, %d] outside its neighbours\' rows [%d, %d): the row-block '
+                             'partition needs a banded ordering (RCM)' % (r, cmin, cmax, lo_limit, hi_limit))
+        plans.append({'lo': lo, 'hi': hi, 'n_local': hi - lo, 'ghost_lo': max(0, lo - cmin), 'ghost_hi': max(0, cmax + 1 - hi)})
+    for r, p in enumerate(plans):
+        p['send_lo'] = plans[r - 1]['ghost_hi'] if r > 0 else 0
+        p['send_hi'] = plans[r + 1]['ghost_lo'] if r < world - 1 else 0
+        if p['send_lo'] > p['n_local'] or p['send_hi'] > p['n_local']:
+            raise ValueError('rank %d: a neighbour needs more ghost rows than the block has' % r)
+        p['lower_window_index'] = plans[r - 1]['ghost_lo'] + plans[r - 1]['n_local'] if r > 0 else -1
+        p['upper_window_index'] = plans[r + 1]['ghost_lo'] - p['send_hi'] if r < world - 1 else -1
+        p['window'] = p['ghost_lo'] + p['n_local'] + p['ghost_hi']
+    return plans
+
+
+class PartitionedSemiImplicitFEM:
+    """One rank's block of the reference's semi-implicit monodomain step
+
+        (MASS + dt*STIFFNESS) U1 = MASS (U0 + dt (differentiate(U0) + I0))
+        (gpuSolve/physics/monodomainSolver.py:98-108; heatSolver.py:127-135 when model='none')
+
+    with the nodes split into contiguous row blocks (banded / RCM order).  Two launches per time step and
+    per rank: the ionic update over the rank's WINDOW (owned + ghost nodes: ghost gates are advanced
+    redundantly, bit-identically to their owner, so RHS0 needs no exchange) and one persistent cooperative
+    PCG kernel that talks to the other ranks through NVLink peer memory (pdx_pcg_part_solve).
+
+    rowptr, col, mval, kval: CSR rows [lo, hi) of MASS and STIFFNESS on one pattern (rowptr local, col GLOBAL).
+
+    Ranks are either the processes of a torch.distributed group (workspaces in symmetric memory), or -
+    ``connect=False`` + ``PartitionedSemiImplicitFEM.connect_local([...])`` - several instances inside one
+    process on one GPU, each on its own stream with ``max_blocks`` capped so that the cooperative grids fit
+    side by side (how the protocol is tested on a single GPU).
+    """
+
+    def __init__(self, n_global, rowptr, col, mval, kval, dt, model='fenton4v', params=None, rank=0, world=1,
+                 group=None, math='fast', device=None, maxiter=100, toll=1e-5, check_every=5, max_blocks=0,
+                 timeout_ms=0, stream=None, connect=True):
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != 'cuda':
+            raise L.PdxError('PartitionedSemiImplicitFEM needs a CUDA device: there is no CPU path')
+        if world > L.PART_MAX_WORLD:
+            raise ValueError('at most %d ranks' % L.PART_MAX_WORLD)
+        self.n, self.rank, self.world, self.group = int(n_global), rank, world, group
+        self.blocks = row_blocks(self.n, world)
+        self.lo, self.hi = self.blocks[rank]
+        self.nloc = self.hi - self.lo
+        self._rowptr_h = np.ascontiguousarray(rowptr, dtype=np.int32)
+        self._col_h = np.ascontiguousarray(col, dtype=np.int64)
+        if self._rowptr_h.shape[0] != self.nloc + 1:
+            raise ValueError('rowptr must describe the %d rows of this rank' % self.nloc)
+        mval = np.ascontiguousarray(mval, dtype=np.float32)
+        kval = np.ascontiguousarray(kval, dtype=np.float32)
+        # A = MASS + dt*STIFFNESS value-wise on the shared pattern, fp32 (csr_axpby, globalMatrices.py:465-492)
+        self._aval_h = mval * np.float32(1.0) + kval * np.float32(dt)
+        self._mval_h = mval
+        rows = np.repeat(np.arange(self.lo, self.hi, dtype=np.int64), np.diff(self._rowptr_h))
+        diag = rows == self._col_h
+        minv = np.zeros(self.nloc, dtype=np.float32)          # JacobiPrecond: zeros where the diagonal is absent
+        minv[rows[diag] - self.lo] = np.float32(1.0) / self._aval_h[diag]
+        self._minv_h = minv
+        self.col_range = (int(self._col_h.min()), int(self._col_h.max()))
+        self.dt, self.maxiter, self.toll, self.check_every = dt, int(maxiter), float(toll), int(check_every)
+        self.max_blocks, self.timeout_ms = int(max_blocks), int(timeout_ms)
+        self.model_id = _MODEL_IDS[model]
+        self.math_id = _MATH_IDS[math]
+        p = (L.default_params(self.model_id) if params is None else list(params)) if self.model_id != L.MODEL_NONE else []
+        self._params = (C.c_float * L.MAX_PARAMS)(*p)
+        self.stream = stream
+        self._h = None
+        self._symm = None
+        self.nsteps_done = 0
+        if not connect:
+            return
+        if world == 1:
+            self._plan_and_allocate([self.col_range])
+            self._attach([self.ws.data_ptr()])
+            return
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        mine = torch.tensor(self.col_range, dtype=torch.int64, device=self.device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine, group=group)
+        self._plan_and_allocate([tuple(int(v) for v in t.tolist()) for t in allr], symmetric=True)
+        self._symm = symm.rendezvous(self.ws, group if group is not None else dist.group.WORLD)
+        self._attach([int(q) for q in self._symm.buffer_ptrs])
+        self._symm.barrier(channel=0)                       # every rank has cleared its block before any solve
+        torch.cuda.synchronize(self.device)
+
+    @staticmethod
+    def connect_local(ranks):
+        """Wire instances that live in ONE process on ONE GPU (plain device pointers as peers)."""
+        ranks = sorted(ranks, key=lambda f: f.rank)
+        ranges = [f.col_range for f in ranks]
+        for f in ranks:
+            f._plan_and_allocate(ranges)
+        ptrs = [f.ws.data_ptr() for f in ranks]
+        for f in ranks:
+            f._attach(ptrs)
+        torch.cuda.synchronize()
+
+    # ---- setup ------------------------------------------------------------------------------
+    def _plan_and_allocate(self, ranges, symmetric=False):
+        plans = plan_windows(self.blocks, ranges)
+        self.plan = plans[self.rank]
+        self.max_window = max(p['window'] for p in plans)
+        self.glo, self.ghi, self.window = self.plan['ghost_lo'], self.plan['ghost_hi'], self.plan['window']
+        nbytes = int(L.lib().pdx_pcg_part_workspace_bytes(self.max_window))
+        if symmetric:
+            import torch.distributed._symmetric_memory as symm
+            self.ws = symm.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        else:
+            self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        self.ws.zero_()
+
+    def _attach(self, peer_ptrs):
+        dev = self.device
+        self.rowptr = torch.from_numpy(self._rowptr_h).to(dev)
+        self.col = torch.from_numpy((self._col_h - (self.lo - self.glo)).astype(np.int32)).to(dev)   # window-local
+        self.aval = torch.from_numpy(self._aval_h).to(dev)
+        self.mval = torch.from_numpy(self._mval_h).to(dev)
+        self.minv = torch.from_numpy(self._minv_h).to(dev)
+        d = L.PcgPartDesc()
+        d.n_local, d.ghost_lo, d.ghost_hi = self.nloc, self.glo, self.ghi
+        d.rank, d.world = self.rank, self.world
+        d.send_lo, d.send_hi = self.plan['send_lo'], self.plan['send_hi']
+        d.lower_window_index, d.upper_window_index = self.plan['lower_window_index'], self.plan['upper_window_index']
+        d.max_blocks, d.timeout_ms = self.max_blocks, self.timeout_ms
+        d.rowptr, d.col, d.aval = self.rowptr.data_ptr(), self.col.data_ptr(), self.aval.data_ptr()
+        d.mval, d.minv = self.mval.data_ptr(), self.minv.data_ptr()
+        arr = (C.c_void_p * self.world)(*peer_ptrs)
+        h = C.c_void_p()
+        L.check(L.lib().pdx_pcg_part_create(C.byref(d), arr, self.max_window, C.byref(h)))
+        self._h = h
+        base = self.ws.data_ptr()
+
+        def view(ptr):
+            off = int(ptr) - base
+            return self.ws[off:off + 4 * self.window].view(torch.float32)
+
+        self.U = view(L.lib().pdx_pcg_part_x(h))             # potential window: guess in, solution out
+        self.rhs0 = view(L.lib().pdx_pcg_part_rhs0(h))
+        self.U.fill_(-80.0 if self.model_id != L.MODEL_NONE else 0.0)
+        self.states = [torch.full((self.window,), v, dtype=torch.float32, device=dev) for v in STATE_INIT[self.model_id]]
+        self._states_arr = L.ptr_array(self.states)
+        self.info = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.blocks_per_grid = int(L.lib().pdx_pcg_part_blocks(h))
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                L.lib().pdx_pcg_part_destroy(self._h)
+        except Exception:
+            pass
+        self._h = None
+
+    # ---- data -------------------------------------------------------------------------------
+    def window_of(self, global_array):
+        """This rank's window (ghosts included) of a global nodal array, as a device tensor."""
+        g = np.ascontiguousarray(global_array, dtype=np.float32).reshape(-1)
+        return torch.from_numpy(g[self.lo - self.glo:self.hi + self.ghi].copy()).to(self.device)
+
+    def set_global_U(self, U):
+        self.U.copy_(self.window_of(U))
+        torch.cuda.current_stream().synchronize()           # the solves may run on another stream
+
+    def owned_U(self):
+        return self.U[self.glo:self.glo + self.nloc]
+
+    def owned_state(self, i):
+        return self.states[i][self.glo:self.glo + self.nloc]
+
+    def last_solve(self):
+        """(iterations, ||r||^2, flags) of the last solve; synchronises.  Raises when a peer timed out."""
+        if self.stream is not None:
+            self.stream.synchronize()
+        h = self.info.cpu().numpy()
+        flags = int(h[2])
+        if flags & 4:
+            raise L.PdxError('partitioned PCG: a peer rank did not answer within the timeout')
+        return int(h[0]), float(h[1:2].view(np.float32)[0]), flags
+
+    # ---- stepping ---------------------------------------------------------------------------
+    def solve(self, b=None):
+        """A x = b on the potential window (b: owned rows; None: b = MASS * rhs0 window)."""
+        L.check(L.lib().pdx_pcg_part_solve(self._h, L.ptr(b), self.maxiter, self.toll, self.check_every,
+                                           L.ptr(self.info), L.stream_ptr(self.stream)))
+
+    def step(self, nsteps=1, I0=None):
+        """nsteps semi-implicit time steps; I0: window-length forcing (window_of(global I0)) or None."""
+        lib = L.lib()
+        dt32 = float(np.float32(self.dt))
+        sp = L.stream_ptr(self.stream)
+        for _ in range(nsteps):
+            if self.model_id == L.MODEL_NONE:
+                with torch.cuda.stream(self.stream or torch.cuda.current_stream()):
+                    if I0 is None:
+                        self.rhs0.copy_(self.U)
+                    else:
+                        torch.add(self.U, I0, alpha=dt32, out=self.rhs0)
+            else:
+                # RHS0 = U + dt*(differentiate(U) + I0) over the whole window   (monodomainSolver.py:100-103)
+                L.check(lib.pdx_ionic_step(self.model_id, self.math_id, self._params, None, self.window, L.ptr(self.U),
+                                           self._states_arr, None, dt32, L.ptr(I0), L.ptr(self.rhs0), sp))
+            L.check(lib.pdx_pcg_part_solve(self._h, None, self.maxiter, self.toll, self.check_every, L.ptr(self.info), sp))
+        self.nsteps_done += nsteps

@@ -60,10 +60,11 @@ _CELL_TETS = ((0, 1, 2, 6), (0, 1, 6, 5), (0, 2, 3, 6), (0, 3, 7, 6), (0, 5, 6, 
 
 
 def _cell_matrices(h, sigma):
-    """P1 stiffness (8x8) and lumped mass (8) of ONE hexahedral cell of tetrahedral_box with edge
-    lengths h = (hx, hy, hz) and isotropic conductivity sigma (float64)."""
+    """P1 stiffness (8x8), lumped mass (8) and consistent mass (8x8) of ONE hexahedral cell of
+    tetrahedral_box with edge lengths h = (hx, hy, hz) and isotropic conductivity sigma (float64)."""
     X = _CELL_CORNERS * np.asarray(h, dtype=np.float64)
     K = np.zeros((8, 8))
+    M = np.zeros((8, 8))
     m = np.zeros(8)
     for tet in _CELL_TETS:
         P = X[list(tet)]
@@ -75,24 +76,27 @@ def _cell_matrices(h, sigma):
             m[tet[a]] += vol / 4.0                  # row sum of the consistent P1 mass matrix
             for b in range(4):
                 K[tet[a], tet[b]] += Kt[a, b]
-    return K, m
+                M[tet[a], tet[b]] += vol / 20.0 * (2.0 if a == b else 1.0)   # P1 tetrahedron mass matrix
+    return K, m, M
 
 
 def _pair_in_cell_tet(a, b):
     return any(a in t and b in t for t in _CELL_TETS)
 
 
-def structured_tet_operator(nx, ny, nz, h=(1.0, 1.0, 1.0), sigma=1.0, row_lo=0, row_hi=None):
+def structured_tet_operator(nx, ny, nz, h=(1.0, 1.0, 1.0), sigma=1.0, row_lo=0, row_hi=None, consistent_mass=False):
     """Rows [row_lo, row_hi) of the P1 stiffness matrix K (CSR, global column indices, fp32) and of the
     lumped mass M_L of tetrahedral_box(nx, ny, nz) WITHOUT materialising the mesh: the mesh is a
     translation of one 6-tetrahedron cell, so K(row, row + d) = sum over the cell corners (a, b) with
     offset(b) - offset(a) = d of Kcell[a, b] * [the cell based at node - offset(a) exists].
     This is what lets config 5 (272^3 = 2.0e7 nodes, 1.2e8 tetrahedra) be set up per rank in seconds;
     tests/test_fem_partition_cpu.py checks it against the general element-by-element assembly.
-    Returns rowptr int32 [n+1], col int32 [nnz], kval fp32 [nnz], mlump fp32 [n] (n = row_hi - row_lo)."""
+    Returns rowptr int32 [n+1], col int32 [nnz], kval fp32 [nnz], mlump fp32 [n] (n = row_hi - row_lo);
+    with consistent_mass=True also mval fp32 [nnz], the consistent P1 mass matrix on the same pattern
+    (the MASS of the semi-implicit step, fem_dist.PartitionedSemiImplicitFEM)."""
     n_global = nx * ny * nz
     row_hi = n_global if row_hi is None else row_hi
-    Kc, mc = _cell_matrices(h, sigma)
+    Kc, mc, Mc = _cell_matrices(h, sigma)
     rows = np.arange(row_lo, row_hi, dtype=np.int64)
     i, rem = np.divmod(rows, ny * nz)
     j, k = np.divmod(rem, nz)
@@ -115,14 +119,18 @@ def structured_tet_operator(nx, ny, nz, h=(1.0, 1.0, 1.0), sigma=1.0, row_lo=0, 
         groups.setdefault(d, []).append((a, b))
     offs = sorted(groups, key=lambda d: (d[0] * ny + d[1]) * nz + d[2])
     vals = np.zeros((rows.shape[0], len(offs)))
+    mvals = np.zeros((rows.shape[0], len(offs))) if consistent_mass else None
     mask = np.zeros((rows.shape[0], len(offs)), dtype=bool)
     cols = np.zeros((rows.shape[0], len(offs)), dtype=np.int64)
     for c, d in enumerate(offs):
         cols[:, c] = rows + (d[0] * ny + d[1]) * nz + d[2]
         for a, b in groups[d]:
             vals[:, c] += Kc[a, b] * valid[a]
+            if consistent_mass:
+                mvals[:, c] += Mc[a, b] * valid[a]
             mask[:, c] |= valid[a] & _pair_in_cell_tet(a, b)
     rowptr = np.zeros(rows.shape[0] + 1, dtype=np.int64)
     np.cumsum(mask.sum(axis=1), out=rowptr[1:])
-    return (rowptr.astype(np.int32), cols[mask].astype(np.int32), vals[mask].astype(np.float32),
-            mlump.astype(np.float32))
+    out = (rowptr.astype(np.int32), cols[mask].astype(np.int32), vals[mask].astype(np.float32),
+           mlump.astype(np.float32))
+    return out + (mvals[mask].astype(np.float32),) if consistent_mass else out

@@ -65,3 +65,41 @@ def test_exchange_plan_on_a_banded_operator():
             assert (g < a + s_lo) if owner > r else (g >= b - s_hi)
     with pytest.raises(ValueError):                       # ghosts two blocks away: not banded enough
         plan_exchange(row_blocks(n, 9), [(max(lo - 3 * band, 0), min(hi + 3 * band, n) - 1) for lo, hi in row_blocks(n, 9)], 4)
+
+
+def test_window_plan_of_the_semi_implicit_partition():
+    from pdensorflow_b200.fem_dist import plan_windows
+    nx, ny, nz, world = 9, 4, 5, 3
+    n = nx * ny * nz
+    blocks = row_blocks(n, world)
+    ranges, cols = [], []
+    for lo, hi in blocks:
+        _, ci, _, _ = structured_tet_operator(nx, ny, nz, row_lo=lo, row_hi=hi)
+        ranges.append((int(ci.min()), int(ci.max())))
+        cols.append(ci)
+    plans = plan_windows(blocks, ranges)
+    for r, (p, (lo, hi)) in enumerate(zip(plans, blocks)):
+        assert p['window'] == p['ghost_lo'] + (hi - lo) + p['ghost_hi']
+        assert (p['ghost_lo'] == 0) == (r == 0) and (p['ghost_hi'] == 0) == (r == world - 1)
+        local = cols[r].astype(np.int64) - (lo - p['ghost_lo'])         # window-local columns stay inside the window
+        assert local.min() >= 0 and local.max() < p['window']
+        if r > 0:                                                       # my row i sits at lower_window_index + i below
+            q = plans[r - 1]
+            assert p['send_lo'] == q['ghost_hi'] and p['lower_window_index'] == q['ghost_lo'] + q['n_local']
+        if r < world - 1:                                               # my row n - send_hi + j sits at upper_window_index + j above
+            q = plans[r + 1]
+            assert p['send_hi'] == q['ghost_lo']
+            g_first = hi - p['send_hi']                                 # global index of the first row sent up
+            assert g_first - (q['lo'] - q['ghost_lo']) == p['upper_window_index']
+    with pytest.raises(ValueError):
+        plan_windows(row_blocks(n, 9), [(max(lo - 200, 0), min(hi + 200, n) - 1) for lo, hi in row_blocks(n, 9)])
+
+
+def test_structured_consistent_mass_matches_assembly():
+    nx, ny, nz, h = 4, 5, 3, (0.3, 0.2, 0.5)
+    P, E, F = tetrahedral_box(nx, ny, nz, Lx=(nx - 1) * h[0], Ly=(ny - 1) * h[1], Lz=(nz - 1) * h[2])
+    m = ofem.assemble(P, E, F, {1: 1.0}, {1: 1.0})
+    rp, ci, kv, ml, mv = structured_tet_operator(nx, ny, nz, h, 1.0, consistent_mass=True)
+    assert np.array_equal(ci, m['col'])
+    np.testing.assert_allclose(mv, m['mass'], rtol=0, atol=2e-6 * np.abs(m['mass']).max())
+    np.testing.assert_allclose(np.add.reduceat(mv.astype(np.float64), rp[:-1]), ml, rtol=1e-5)

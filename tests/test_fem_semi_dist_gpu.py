@@ -1,0 +1,209 @@
+"""Row-block partitioned SEMI-IMPLICIT FEM step (FEM): the persistent cooperative PCG
+kernel whose ranks talk through peer memory (pdx_pcg_part_solve).  One rank against the single-GPU PCG and the
+oracle; 2/3 ranks sharing ONE GPU (plain device pointers as peers, one stream per rank) and 2 ranks on 2 GPUs
+(NVLink symmetric memory) against one rank; a missing peer is reported, not waited for."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DIMS, H, SIGMA, DT = (13, 6, 8), (0.25, 0.25, 0.25), 1e-3, 0.1
+TOL_CG = 5e-5            # two correct CG implementations agree to a small multiple of the stopping tolerance
+
+
+def _same_iterations(a, b):
+    """Iteration counts of two correct implementations: equal, except that a residual sitting on the stopping
+    threshold may tip the batched test (every 5 iterations) the other way on a few steps."""
+    d = np.abs(np.asarray(a) - np.asarray(b))
+    return len(a) == len(b) and d.max() <= 5 and (d > 0).sum() <= max(2, len(a) // 5)
+
+
+def _operator(lo=0, hi=None):
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    return structured_tet_operator(*DIMS, H, SIGMA, lo, hi, consistent_mass=True)
+
+
+def _initial():
+    n = DIMS[0] * DIMS[1] * DIMS[2]
+    U = np.full(n, -80.0, dtype=np.float32)
+    U[: 2 * DIMS[1] * DIMS[2]] = 20.0
+    return U
+
+
+def _make(rank=0, world=1, **kw):
+    from pdensorflow_b200.fem_dist import PartitionedSemiImplicitFEM, row_blocks
+    n = DIMS[0] * DIMS[1] * DIMS[2]
+    lo, hi = row_blocks(n, world)[rank]
+    rp, ci, kv, ml, mv = _operator(lo, hi)
+    return PartitionedSemiImplicitFEM(n, rp, ci, mv, kv, DT, rank=rank, world=world, **kw)
+
+
+def test_one_rank_solve_matches_single_gpu_pcg(cuda):
+    from pdensorflow_b200 import _lib as L
+    n = DIMS[0] * DIMS[1] * DIMS[2]
+    fem = _make(model='none', maxiter=400, toll=1e-6)
+    rng = np.random.default_rng(3)
+    xs = rng.standard_normal(n).astype(np.float32)
+    b = torch.from_numpy(xs).cuda()
+    # single-GPU persistent PCG on the same matrix
+    h = C.c_void_p()
+    L.check(L.lib().pdx_pcg_create(n, L.ptr(fem.rowptr), L.ptr(fem.col), L.ptr(fem.aval), L.ptr(fem.minv), C.byref(h)))
+    x1 = torch.zeros(n, device='cuda')
+    info = torch.zeros(4, dtype=torch.int32, device='cuda')
+    L.check(L.lib().pdx_pcg_solve(h, L.ptr(b), L.ptr(x1), 400, 1e-6, 5, L.ptr(info), L.stream_ptr()))
+    fem.U.zero_()
+    fem.solve(b)
+    torch.cuda.synchronize()
+    it, res, flags = fem.last_solve()
+    L.lib().pdx_pcg_destroy(h)
+    assert flags == 0 and abs(it - int(info[0].item())) <= 5 and res < 1e-12
+    assert rel_l2(fem.owned_U().cpu().numpy(), x1.cpu().numpy()) <= 1e-5
+    # and it solves the system
+    import scipy.sparse as sp
+    A = sp.csr_matrix((fem.aval.cpu().numpy().astype(np.float64), fem.col.cpu().numpy(), fem.rowptr.cpu().numpy()), shape=(n, n))
+    assert np.linalg.norm(A @ fem.owned_U().cpu().numpy().astype(np.float64) - xs) <= 1e-5 * np.linalg.norm(xs)
+
+
+def _oracle_steps(nsteps):
+    from oracle import fem as ofem
+    from oracle import ionic as oi
+    rp, ci, kv, ml, mv = _operator()
+    n = len(ml)
+    A = ofem.csr_axpby(mv, 1.0, kv, DT)
+    minv = ofem.jacobi(rp, ci, A, n)
+    mo = oi.Fenton4v()
+    mo._dt = DT
+    U = _initial()
+    mo.initialize_state_variables(U[:, None])
+    its = []
+    for _ in range(nsteps):
+        rhs0 = U + np.float32(DT) * mo.differentiate(U[:, None])[:, 0]
+        rhs = ofem.spmv(rp, ci, mv, rhs0)
+        U, nit, _ = ofem.pcg(rp, ci, A, minv, rhs, U, 100, 1e-5)
+        its.append(nit)
+    return U, its
+
+
+def test_one_rank_steps_match_oracle(cuda):
+    nsteps = 25
+    Uo, its = _oracle_steps(nsteps)
+    fem = _make(math='exact')
+    fem.set_global_U(_initial())
+    got_its = []
+    for _ in range(nsteps):
+        fem.step(1)
+        got_its.append(fem.last_solve()[0])
+    got = fem.owned_U().cpu().numpy()
+    assert np.isfinite(got).all() and got.max() > 0.0
+    assert rel_l2(got, Uo) <= TOL_CG, rel_l2(got, Uo)
+    assert _same_iterations(got_its, its), (got_its, its)
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_ranks_sharing_one_gpu_match_one_rank(cuda, world):
+    from pdensorflow_b200.fem_dist import PartitionedSemiImplicitFEM
+    nsteps = 20
+    ref = _make(math='exact')
+    ref.set_global_U(_initial())
+    ref_its = []
+    for _ in range(nsteps):
+        ref.step(1)
+        ref_its.append(ref.last_solve()[0])
+    Uref, Vref = ref.owned_U().cpu().numpy(), ref.owned_state(0).cpu().numpy()
+    ranks = [_make(r, world, math='exact', connect=False, max_blocks=16, timeout_ms=5000, stream=torch.cuda.Stream())
+             for r in range(world)]
+    PartitionedSemiImplicitFEM.connect_local(ranks)
+    for f in ranks:
+        assert (f.glo > 0) == (f.rank > 0) and (f.ghi > 0) == (f.rank < world - 1)
+        f.set_global_U(_initial())
+    its = [[] for _ in ranks]
+    for _ in range(nsteps):
+        for f in ranks:                  # every rank's two launches go to its own stream; the kernels meet on the device
+            f.step(1)
+        for k, f in enumerate(ranks):
+            its[k].append(f.last_solve()[0])
+    torch.cuda.synchronize()
+    assert all(i == its[0] for i in its)                # same convergence decision on every rank
+    assert _same_iterations(its[0], ref_its), (its[0], ref_its)
+    for f in ranks:
+        assert rel_l2(f.owned_U().cpu().numpy(), Uref[f.lo:f.hi]) <= TOL_CG
+        assert np.array_equal(f.owned_state(0).cpu().numpy(), Vref[f.lo:f.hi]) or \
+            rel_l2(f.owned_state(0).cpu().numpy(), Vref[f.lo:f.hi]) <= TOL_CG
+    # ghosts are recomputed, never exchanged: they must equal the owner's values BITWISE
+    for a, b in zip(ranks[:-1], ranks[1:]):
+        assert np.array_equal(a.U[a.glo + a.nloc:].cpu().numpy(), b.owned_U()[:a.ghi].cpu().numpy())
+        assert np.array_equal(b.U[:b.glo].cpu().numpy(), a.owned_U()[a.nloc - b.glo:].cpu().numpy())
+        assert np.array_equal(a.states[0][a.glo + a.nloc:].cpu().numpy(), b.owned_state(0)[:a.ghi].cpu().numpy())
+
+
+def test_missing_peer_is_reported_not_waited_for(cuda):
+    from pdensorflow_b200 import _lib as L
+    from pdensorflow_b200.fem_dist import PartitionedSemiImplicitFEM
+    ranks = [_make(r, 2, connect=False, max_blocks=16, timeout_ms=200) for r in range(2)]
+    PartitionedSemiImplicitFEM.connect_local(ranks)
+    ranks[0].set_global_U(_initial())
+    ranks[0].step(1)                                    # rank 1 never launches
+    torch.cuda.synchronize()
+    with pytest.raises(L.PdxError):
+        ranks[0].last_solve()
+
+
+def _worker(rank, world, port, nsteps, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        fem = _make(rank, world, math='exact', timeout_ms=20000)
+        fem.set_global_U(_initial())
+        its = []
+        for _ in range(nsteps):
+            fem.step(1)
+            its.append(fem.last_solve()[0])
+        torch.cuda.synchronize()
+        q.put((rank, fem.lo, fem.owned_U().cpu().numpy(), its))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_match_one_rank(cuda):
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
+    nsteps = 20
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        got = [q.get(timeout=120) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    ref = _make(math='exact')
+    ref.set_global_U(_initial())
+    ref_its = []
+    for _ in range(nsteps):
+        ref.step(1)
+        ref_its.append(ref.last_solve()[0])
+    Uref = ref.owned_U().cpu().numpy()
+    for rank, lo, U, its in got:
+        assert _same_iterations(its, ref_its), (its, ref_its)
+        assert rel_l2(U, Uref[lo:lo + U.shape[0]]) <= TOL_CG
