@@ -45,8 +45,11 @@ enum { PDX_LAP_HOMOG = 0, PDX_LAP_CONV = 1, PDX_LAP_HETEROG = 2, PDX_LAP_ANISO =
  * multiplies, FMA contraction and ex2/rcp-based tanh (|err| ~1e-7); meets the
  * north-star tolerance (rel-L2 <= 1e-5) and is what bench.py times. */
 enum { PDX_MATH_EXACT = 0, PDX_MATH_FAST = 1 };
-/* kernel selection for the fused FD step */
-enum { PDX_KERNEL_AUTO = 0, PDX_KERNEL_GENERIC = 1, PDX_KERNEL_TMA = 2 };
+/* kernel selection for the fused FD step.  RESIDENT: 2-D grids that fit in the shared memory of the
+ * SMs (up to ~1.5 M nodes with Fenton-Karma) are advanced by ONE launch per pdx_fd_step call that keeps
+ * U and the gates on chip for all nsteps (pdx_fd_resident.cu); homogeneous operator, closed-form
+ * models.  AUTO picks it for such grids when a call asks for >= 8 steps outside stream capture. */
+enum { PDX_KERNEL_AUTO = 0, PDX_KERNEL_GENERIC = 1, PDX_KERNEL_TMA = 2, PDX_KERNEL_RESIDENT = 3 };
 
 #define PDX_MAX_PARAMS 24
 #define PDX_MAX_STATES 4          /* closed-form models (FENTON4V / MMS2V / MS2V) */
@@ -152,8 +155,11 @@ int pdx_fd_plan_set_lut(pdx_fd_plan* p, const pdx_lut_model* m);
 void pdx_fd_desc_init(pdx_fd_desc* d);                      /* zero + defaults */
 int  pdx_fd_plan_create(const pdx_fd_desc* d, pdx_fd_plan** out);
 void pdx_fd_plan_destroy(pdx_fd_plan* p);
-/* which kernel a plan resolved to (PDX_KERNEL_GENERIC / PDX_KERNEL_TMA) */
+/* which kernel a plan resolved to for single steps (PDX_KERNEL_GENERIC / PDX_KERNEL_TMA /
+ * PDX_KERNEL_RESIDENT) */
 int  pdx_fd_plan_kernel(const pdx_fd_plan* p);
+/* 1 when multi-step calls on this plan can use the SM-resident kernel */
+int  pdx_fd_plan_resident_capable(const pdx_fd_plan* p);
 /* number of kernel launches issued through this plan so far */
 int64_t pdx_fd_plan_launches(const pdx_fd_plan* p);
 

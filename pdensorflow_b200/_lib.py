@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libpdx.so')
 MODEL_NONE, MODEL_FENTON4V, MODEL_MMS2V, MODEL_MS2V, MODEL_CRN, MODEL_TTP = 0, 1, 2, 3, 4, 5
 LAP_HOMOG, LAP_CONV, LAP_HETEROG, LAP_ANISO = 0, 1, 2, 3
 MATH_EXACT, MATH_FAST = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TMA = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TMA, KERNEL_RESIDENT = 0, 1, 2, 3
 MAX_PARAMS, MAX_STATES = 24, 4
 LUT_MAX_STATES, LUT_MAX_CONSTS = 24, 64
 
@@ -72,6 +72,7 @@ _SIGNATURES = {
     'pdx_fd_plan_create': (C.c_int, [C.POINTER(FdDesc), C.POINTER(_P)]),
     'pdx_fd_plan_destroy': (None, [_P]),
     'pdx_fd_plan_kernel': (C.c_int, [_P]),
+    'pdx_fd_plan_resident_capable': (C.c_int, [_P]),
     'pdx_fd_plan_launches': (C.c_int64, [_P]),
     'pdx_fd_step': (C.c_int, [_P, _P, _P, C.POINTER(_P), _P, C.c_int, _P]),
     'pdx_fd_step_mirror': (C.c_int, [_P, _P, _P, C.POINTER(_P), _P, _P, _P, _P]),

@@ -16,7 +16,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 BUILD = os.path.join(HERE, 'build')
 LIB = os.path.join(PKG, 'libpdx.so')
-SOURCES = ['pdx_api.cu', 'pdx_fd_generic.cu', 'pdx_fd_tma.cu', 'pdx_fem.cu', 'pdx_fem_part.cu', 'pdx_ionic_lut.cu']
+SOURCES = ['pdx_api.cu', 'pdx_fd_generic.cu', 'pdx_fd_tma.cu', 'pdx_fd_resident.cu', 'pdx_fem.cu', 'pdx_fem_part.cu', 'pdx_ionic_lut.cu']
 # per-source flags: the lookup-table models are evaluated op-for-op (no FMA contraction)
 EXTRA = {'pdx_ionic_lut.cu': ['-fmad=false']}
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']

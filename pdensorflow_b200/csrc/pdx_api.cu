@@ -97,6 +97,18 @@ struct pdx_fd_plan {
     std::unordered_map<const void*, CUtensorMap> smaps;   // state arrays (box without halo)
     bool tma_states;
     int64_t launches;
+    // SM-resident multi-step path (2-D grids that fit on chip)
+    bool resident_ok;
+    bool resident_auto;
+    bool want_resident;
+    ResidentGeom rg;
+    unsigned int* res_flags;
+    float* res_halo;
+    unsigned int res_base;
+    ~pdx_fd_plan() {
+        if (res_flags) cudaFree(res_flags);
+        if (res_halo) cudaFree(res_halo);
+    }
 };
 
 static int get_state_map(pdx_fd_plan* p, const float* ptr, const CUtensorMap** out) {
@@ -257,7 +269,15 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     }
     int kernel = d.kernel;
     const bool tma_ok = fd_tma_supported(d) && !is_lut_model(d.model) && d.lap_kind != PDX_LAP_ANISO;
-    if (kernel == PDX_KERNEL_AUTO) kernel = tma_ok ? PDX_KERNEL_TMA : PDX_KERNEL_GENERIC;
+    ResidentGeom rg{};
+    const bool res_ok = fd_resident_plan(d, &rg);
+    if (kernel == PDX_KERNEL_RESIDENT && !res_ok) {
+        set_error("pdx_fd_plan_create: the resident kernel takes 2-D grids (nz <= 1024) that fit in the SMs' shared "
+                  "memory, homogeneous operator, closed-form models, no Dirichlet pad");
+        return 1;
+    }
+    const bool want_resident = kernel == PDX_KERNEL_RESIDENT;
+    if (kernel == PDX_KERNEL_AUTO || want_resident) kernel = tma_ok ? PDX_KERNEL_TMA : PDX_KERNEL_GENERIC;
     if (kernel == PDX_KERNEL_TMA && !tma_ok) {
         set_error("pdx_fd_plan_create: TMA kernel needs nz % 4 == 0, no Dirichlet, no EXACT conv");
         return 1;
@@ -267,6 +287,23 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     p->d = d;
     p->kernel = kernel;
     p->launches = 0;
+    p->resident_ok = res_ok;
+    p->resident_auto = false;
+    p->rg = rg;
+    p->res_flags = nullptr;
+    p->res_halo = nullptr;
+    p->res_base = 0;
+    if (res_ok && (want_resident || d.kernel == PDX_KERNEL_AUTO)) {
+        const char* e = std::getenv("PDX_RESIDENT");            // A/B switch: PDX_RESIDENT=0 keeps AUTO on the per-step kernels
+        p->resident_auto = want_resident || !(e && e[0] == '0');
+        if (check_cuda(cudaMalloc(&p->res_flags, sizeof(unsigned int) * (size_t)rg.ncta), "cudaMalloc(resident flags)") ||
+            check_cuda(cudaMemset(p->res_flags, 0, sizeof(unsigned int) * (size_t)rg.ncta), "clear resident flags") ||
+            check_cuda(cudaMalloc(&p->res_halo, sizeof(float) * 4 * (size_t)rg.ncta * d.nz), "cudaMalloc(resident halo)")) {
+            delete p;
+            return 1;
+        }
+    }
+    p->want_resident = want_resident;
     p->has_lut = false;
     p->avec = nullptr;
     {   // states staged by TMA unless PDX_TMA_STATES=0 (A/B switch for profiling)
@@ -313,7 +350,8 @@ int pdx_fd_plan_set_avec(pdx_fd_plan* p, const float* AVEC) {
     p->avec = AVEC;
     return 0;
 }
-int pdx_fd_plan_kernel(const pdx_fd_plan* p) { return p ? p->kernel : -1; }
+int pdx_fd_plan_kernel(const pdx_fd_plan* p) { return p ? (p->want_resident ? (int)PDX_KERNEL_RESIDENT : p->kernel) : -1; }
+int pdx_fd_plan_resident_capable(const pdx_fd_plan* p) { return p && p->resident_ok && p->resident_auto ? 1 : 0; }
 int64_t pdx_fd_plan_launches(const pdx_fd_plan* p) { return p ? p->launches : -1; }
 
 static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const* states, const float* DIFF, int xb,
@@ -386,6 +424,27 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
 int pdx_fd_step(pdx_fd_plan* p, float* U_a, float* U_b, float* const* states, const float* DIFF, int nsteps,
                 void* stream) {
     if (!p) { set_error("pdx_fd_step: null plan"); return 1; }
+    if (p->resident_ok && p->resident_auto && nsteps >= (p->want_resident ? 1 : 8)) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing((cudaStream_t)stream, &cap);
+        if (cap == cudaStreamCaptureStatusNone) {
+            // the whole call is ONE launch: U and the gates stay in shared memory for nsteps steps
+            const int ns = pdx_model_num_states(p->d.model);
+            if (!U_a || !U_b || U_a == U_b) { set_error("pdx_fd_step: U_a/U_b must be distinct non-null buffers"); return 1; }
+            if (ns > 0 && !states) { set_error("pdx_fd_step: states required"); return 1; }
+            FdArgs a = p->base;
+            a.Uin = U_a;
+            a.Uout = (nsteps & 1) ? U_b : U_a;
+            for (int i = 0; i < ns; ++i) {
+                if (!states[i]) { set_error("pdx_fd_step: null state array"); return 1; }
+                a.st[i] = states[i];
+            }
+            const int rc = launch_fd_resident(p->d, a, p->rg, nsteps, p->res_base, p->res_flags, p->res_halo,
+                                              (cudaStream_t)stream);
+            if (!rc) { p->res_base += (unsigned int)nsteps; p->launches += 1; }
+            return rc;
+        }
+    }
     for (int k = 0; k < nsteps; ++k) {
         const float* in = (k & 1) ? U_b : U_a;
         float* outp = (k & 1) ? U_a : U_b;

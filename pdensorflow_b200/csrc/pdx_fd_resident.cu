@@ -1,0 +1,248 @@
+// pdx_fd_resident.cu - SM-resident multi-step kernel for 2-D grids that fit on chip
+// (BASELINE.json config 2: 1024 x 1024 Fenton-Karma, 10 000 steps).
+//
+// A 1024^2 grid is 4 MB per array: one time step moves 33 MB, which a kernel launch per step turns
+// into ~10 us of launch latency + L2 traffic.  Here the WHOLE grid lives in the shared memory of
+// the SMs for `nsteps` time steps: the rows are dealt out in contiguous strips, one CTA per SM, a
+// thread per column; U (double buffered, with one halo row per side) and the gate variables never
+// leave the SM.  Per step a CTA
+//   1. advances its first and last row (they are what the neighbours wait for),
+//   2. publishes them (2 x nz floats) to a global halo buffer and raises its step flag
+//      (st.release.gpu),
+//   3. advances its interior rows - which hides the flag latency of the neighbours, and
+//   4. at the start of the next step acquires the two neighbour flags and pulls their rows from L2.
+// No grid-wide barrier, no HBM traffic between the first load and the final store.  The CTAs spin
+// on each other, so the kernel is launched cooperatively (co-residency guaranteed).
+//
+// Arithmetic: the same node formulas as the per-step kernels (pdx_math.cuh, evaluation order of
+// pdx_stencil.cuh node_laplacian), so EXACT results are bit-identical to them and to the oracle.
+// Reference: Tests/FD/Fenton/fenton.py:46-53,90-99 transcribed to 2-D (SURVEY.md section 8a, rows
+// B, L2, I-*, T-FD).
+#include <cooperative_groups.h>
+#include <cstdio>
+#include "pdx_internal.h"
+
+namespace pdx {
+namespace {
+
+struct ResArgs {
+    const float* Uin;
+    float* Uout;
+    float* st[PDX_MAX_STATES];
+    int ny, nz;
+    int rows_per_cta;
+    int nsteps;
+    unsigned int base;          // flag value of "nothing published yet" for this launch
+    unsigned int* flags;        // [ncta]
+    float* halo;                // [2][ncta][2][nz]
+    float dt, coef;
+    float hysq, hzsq, rhysq, rhzsq;
+    ModelParams mp;
+};
+
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// wait until *flag has reached `want` (flags only grow; compare modulo 2^32)
+__device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int want) {
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    while ((int)(ld_acquire_gpu_u32(flag) - want) < 0) {
+        if ((++spins & 4095u) == 0) {
+            const unsigned long long t = global_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 5000000000ull) {          // a co-resident CTA never takes 5 s: logic error
+                printf("pdx fd_resident_kernel: CTA %d waited 5 s for a neighbour, aborting\n", (int)blockIdx.x);
+                __trap();
+            }
+        }
+    }
+}
+
+template <int MODEL, int MATH>
+__global__ void __launch_bounds__(1024, 1) fd_resident_kernel(const __grid_constant__ ResArgs a) {
+    extern __shared__ float smem[];
+    constexpr int NS = NStates<MODEL>::value;
+    const int nz = a.nz, ny = a.ny;
+    const int k = threadIdx.x;
+    const int c = blockIdx.x, ncta = gridDim.x;
+    const int j0 = c * a.rows_per_cta;
+    const int rows = min(a.rows_per_cta, ny - j0);
+    const int R = a.rows_per_cta;
+    // shared memory: two U buffers of (R+2) rows (row 0 / rows+1 are the halos), then NS state arrays of R rows
+    const int ustride = (R + 2) * nz;
+    float* Sbuf = smem + (size_t)2 * ustride;
+    const bool active = k < nz;
+
+    if (active) {
+        for (int r = 0; r < rows; ++r) {
+            const size_t g = (size_t)(j0 + r) * nz + k;
+            smem[(r + 1) * nz + k] = a.Uin[g];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) Sbuf[((size_t)s * R + r) * nz + k] = a.st[s][g];
+        }
+        if (j0 > 0) smem[k] = a.Uin[(size_t)(j0 - 1) * nz + k];
+        if (j0 + rows < ny) smem[(rows + 1) * nz + k] = a.Uin[(size_t)(j0 + rows) * nz + k];
+    }
+    __syncthreads();
+
+    // column indices after symmetric pad + enforce_boundary (clamp to the array, then to [1, n-2])
+    const int kc = min(max(k, 1), nz - 2);
+    const int km = min(max(max(k - 1, 0), 1), nz - 2);
+    const int kp = min(max(min(k + 1, nz - 1), 1), nz - 2);
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        float* cur = smem + (s & 1) * ustride;
+        float* nxt = smem + ((s & 1) ^ 1) * ustride;
+        if (s > 0) {
+            // rows published by the neighbours at step s-1
+            if (threadIdx.x == 0 && c > 0) wait_flag(a.flags + c - 1, a.base + s);
+            if (threadIdx.x == 32 && c < ncta - 1) wait_flag(a.flags + c + 1, a.base + s);
+            __syncthreads();
+            const float* hb = a.halo + (size_t)((s - 1) & 1) * ncta * 2 * nz;
+            if (active) {
+                if (c > 0) cur[k] = __ldcg(hb + ((size_t)(c - 1) * 2 + 1) * nz + k);
+                if (c < ncta - 1) cur[(rows + 1) * nz + k] = __ldcg(hb + ((size_t)(c + 1) * 2 + 0) * nz + k);
+            }
+            __syncthreads();
+        }
+        auto update = [&](int r) {
+            const int jg = j0 + r;
+            const int jc = min(max(jg, 1), ny - 2) - j0 + 1;
+            const int jm = min(max(max(jg - 1, 0), 1), ny - 2) - j0 + 1;
+            const int jp = min(max(min(jg + 1, ny - 1), 1), ny - 2) - j0 + 1;
+            const float cval = cur[jc * nz + kc];
+            float lap = lap_axis<MATH>(cur[jm * nz + kc], cval, cur[jp * nz + kc], a.hysq, a.rhysq);
+            lap = madd<MATH>(lap, lap_axis<MATH>(cur[jc * nz + km], cval, cur[jc * nz + kp], a.hzsq, a.rhzsq));
+            float u1 = cval;
+            if (MODEL != PDX_MODEL_NONE) {
+                float st[PDX_MAX_STATES];
+#pragma unroll
+                for (int q = 0; q < NS; ++q) st[q] = Sbuf[((size_t)q * R + r) * nz + k];
+                const float dU = ionic_update<MODEL, MATH>(cur[(r + 1) * nz + k], st, a.mp);    // raw U, not U0
+#pragma unroll
+                for (int q = 0; q < NS; ++q) Sbuf[((size_t)q * R + r) * nz + k] = st[q];
+                u1 = madd<MATH>(u1, mmul<MATH>(a.dt, dU));
+            }
+            const float un = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
+            nxt[(r + 1) * nz + k] = un;
+            return un;
+        };
+        // 1. the rows the neighbours wait for
+        float first = 0.0f, last = 0.0f;
+        if (active) {
+            first = update(0);
+            last = rows > 1 ? update(rows - 1) : first;
+        }
+        // 2. publish them
+        if (s + 1 < a.nsteps) {
+            float* hb = a.halo + (size_t)(s & 1) * ncta * 2 * nz;
+            if (active) {
+                __stcg(hb + ((size_t)c * 2 + 0) * nz + k, first);
+                __stcg(hb + ((size_t)c * 2 + 1) * nz + k, last);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                st_release_gpu_u32(a.flags + c, a.base + s + 1);
+            }
+        }
+        // 3. interior rows
+        if (active)
+            for (int r = 1; r < rows - 1; ++r) update(r);
+        __syncthreads();
+    }
+
+    const float* fin = smem + (a.nsteps & 1) * ustride;
+    if (active) {
+        for (int r = 0; r < rows; ++r) {
+            const size_t g = (size_t)(j0 + r) * nz + k;
+            a.Uout[g] = fin[(r + 1) * nz + k];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) a.st[s][g] = Sbuf[((size_t)s * R + r) * nz + k];
+        }
+    }
+}
+
+template <int MODEL, int MATH>
+const void* kernel_ptr() { return (const void*)fd_resident_kernel<MODEL, MATH>; }
+
+const void* pick_kernel(int model, int math) {
+    const bool ex = math == PDX_MATH_EXACT;
+    switch (model) {
+        case PDX_MODEL_NONE:     return ex ? kernel_ptr<PDX_MODEL_NONE, PDX_MATH_EXACT>() : kernel_ptr<PDX_MODEL_NONE, PDX_MATH_FAST>();
+        case PDX_MODEL_FENTON4V: return ex ? kernel_ptr<PDX_MODEL_FENTON4V, PDX_MATH_EXACT>() : kernel_ptr<PDX_MODEL_FENTON4V, PDX_MATH_FAST>();
+        case PDX_MODEL_MMS2V:    return ex ? kernel_ptr<PDX_MODEL_MMS2V, PDX_MATH_EXACT>() : kernel_ptr<PDX_MODEL_MMS2V, PDX_MATH_FAST>();
+        case PDX_MODEL_MS2V:     return ex ? kernel_ptr<PDX_MODEL_MS2V, PDX_MATH_EXACT>() : kernel_ptr<PDX_MODEL_MS2V, PDX_MATH_FAST>();
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+// Geometry of the resident kernel for a 2-D grid, or false when the grid does not fit on chip /
+// the configuration is not covered (heterogeneous operator, Dirichlet pad, lookup-table models).
+bool fd_resident_plan(const pdx_fd_desc& d, ResidentGeom* g) {
+    if (d.ndim != 2 || d.lap_kind != PDX_LAP_HOMOG || d.dirichlet) return false;
+    if (d.model != PDX_MODEL_NONE && d.model != PDX_MODEL_FENTON4V && d.model != PDX_MODEL_MMS2V && d.model != PDX_MODEL_MS2V)
+        return false;
+    if (d.nz > 1024 || d.nz < 3 || d.ny < 3) return false;
+    int dev = 0, sms = 0, smem_max = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (sms < 1) return false;
+    const int ns = pdx_model_num_states(d.model);
+    const int rows = (d.ny + sms - 1) / sms;                         // strips as even as the SM count allows
+    const size_t bytes = ((size_t)2 * (rows + 2) + (size_t)ns * rows) * d.nz * sizeof(float);
+    if (bytes > (size_t)smem_max) return false;
+    g->rows_per_cta = rows;
+    g->ncta = (d.ny + rows - 1) / rows;
+    g->threads = (d.nz + 31) / 32 * 32;
+    g->smem_bytes = bytes;
+    return true;
+}
+
+int launch_fd_resident(const pdx_fd_desc& d, const FdArgs& f, const ResidentGeom& g, int nsteps, unsigned int base,
+                       unsigned int* flags, float* halo, cudaStream_t s) {
+    const void* fn = pick_kernel(d.model, d.math_mode);
+    if (!fn) { set_error("resident FD kernel: unsupported model"); return 1; }
+    if (check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes),
+                   "resident FD kernel: shared memory opt-in"))
+        return 1;
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, g.threads, g.smem_bytes), "occupancy query") ||
+        per_sm * sms < g.ncta) {
+        if (per_sm * sms < g.ncta) set_error("resident FD kernel: the strips cannot all be resident");
+        return 1;
+    }
+    ResArgs a{};
+    a.Uin = f.Uin; a.Uout = f.Uout;
+    for (int i = 0; i < PDX_MAX_STATES; ++i) a.st[i] = f.st[i];
+    a.ny = d.ny; a.nz = d.nz;
+    a.rows_per_cta = g.rows_per_cta;
+    a.nsteps = nsteps;
+    a.base = base; a.flags = flags; a.halo = halo;
+    a.dt = f.dt; a.coef = f.coef;
+    a.hysq = f.hysq; a.hzsq = f.hzsq; a.rhysq = f.rhysq; a.rhzsq = f.rhzsq;
+    a.mp = f.mp;
+    void* args[] = {&a};
+    count_launch();
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(g.ncta), dim3(g.threads), args, g.smem_bytes, s),
+                      "fd_resident_kernel cooperative launch");
+}
+
+}  // namespace pdx

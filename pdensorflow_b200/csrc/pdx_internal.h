@@ -85,4 +85,13 @@ int  make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int
 void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* box_y, int* box_z);
 int  fd_tma_auto_chunk(const pdx_fd_desc& d);
 
+// SM-resident multi-step kernel for 2-D grids (pdx_fd_resident.cu)
+struct ResidentGeom {
+    int rows_per_cta, ncta, threads;
+    size_t smem_bytes;
+};
+bool fd_resident_plan(const pdx_fd_desc& d, ResidentGeom* g);
+int  launch_fd_resident(const pdx_fd_desc& d, const FdArgs& f, const ResidentGeom& g, int nsteps, unsigned int base,
+                        unsigned int* flags, float* halo, cudaStream_t s);
+
 }  // namespace pdx

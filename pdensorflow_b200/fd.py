@@ -22,7 +22,7 @@ _MODEL_IDS = {None: L.MODEL_NONE, 'none': L.MODEL_NONE, 'heat': L.MODEL_NONE,
               'fenton4v': L.MODEL_FENTON4V, 'mms2v': L.MODEL_MMS2V, 'ms2v': L.MODEL_MS2V}
 _LAP_IDS = {'homog': L.LAP_HOMOG, 'conv': L.LAP_CONV, 'heterog': L.LAP_HETEROG, 'aniso': L.LAP_ANISO}
 _MATH_IDS = {'exact': L.MATH_EXACT, 'fast': L.MATH_FAST}
-_KERNEL_IDS = {'auto': L.KERNEL_AUTO, 'generic': L.KERNEL_GENERIC, 'tma': L.KERNEL_TMA}
+_KERNEL_IDS = {'auto': L.KERNEL_AUTO, 'generic': L.KERNEL_GENERIC, 'tma': L.KERNEL_TMA, 'resident': L.KERNEL_RESIDENT}
 STATE_INIT = {L.MODEL_FENTON4V: (1.0, 1.0, 0.0), L.MODEL_MMS2V: (1.0,), L.MODEL_MS2V: (1.0,), L.MODEL_NONE: ()}
 
 
@@ -151,7 +151,10 @@ class FDStepper:
         handle = C.c_void_p()
         L.check(L.lib().pdx_fd_plan_create(C.byref(d), C.byref(handle)))
         self._plan = handle
-        self.kernel = {L.KERNEL_GENERIC: 'generic', L.KERNEL_TMA: 'tma'}[L.lib().pdx_fd_plan_kernel(handle)]
+        self.kernel = {L.KERNEL_GENERIC: 'generic', L.KERNEL_TMA: 'tma',
+                       L.KERNEL_RESIDENT: 'resident'}[L.lib().pdx_fd_plan_kernel(handle)]
+        # 2-D grids that fit in the SMs' shared memory: a multi-step call is ONE launch (pdx_fd_resident.cu)
+        self.resident = bool(L.lib().pdx_fd_plan_resident_capable(handle))
         self.dt, self.diff = dt, diff
         self.nstates = L.lib().pdx_model_num_states(self.model_id)
         # buffers
@@ -266,7 +269,11 @@ class FDStepper:
         return self._graphs[key]
 
     def run(self, nsteps, block=10):
-        """Advance nsteps using graph-captured blocks of ``block`` steps plus a remainder."""
+        """Advance nsteps using graph-captured blocks of ``block`` steps plus a remainder.  SM-resident
+        plans need neither blocks nor graphs: the whole run is one launch."""
+        if self.resident and nsteps >= 8:
+            self.step(nsteps)
+            return
         block = max(2, block - block % 2)
         nblk, rem = divmod(nsteps, block)
         if nblk:
