@@ -290,9 +290,11 @@ int pdx_fem_explicit_step_sell(int model, int math_mode, const float* params, in
  * Workspace: every rank allocates pdx_pcg_part_workspace_bytes(max_window) bytes (max_window = the
  * largest window over the ranks, so that the layout is the same everywhere) of peer-accessible device
  * memory (symmetric memory / CUDA IPC / plain device memory for ranks that share a GPU) and passes all
- * `world` base pointers, as mapped in THIS process, to create.  The x window (potential: guess on
- * entry, solution on exit, ghosts kept consistent by the kernel) and the rhs0 window live inside it.
- * All ranks must have returned from create before any rank calls solve (create clears the block). */
+ * `world` base pointers, as mapped in THIS process, to create.  It holds what the neighbours write:
+ * the exchange words and the p / z windows.  x, b and rhs0 are ordinary caller-owned device arrays.
+ * All ranks must have returned from create before any rank calls solve (create clears the block).
+ * world = 1 with plain device memory is the single-GPU solver for large systems (SELL-32 storage,
+ * gpuSolve.linearsolvers.ConjGrad uses it above 10^5 rows). */
 #define PDX_PART_MAX_WORLD 16
 typedef struct pdx_pcg_part_desc {
     int32_t n_local, ghost_lo, ghost_hi;
@@ -301,6 +303,9 @@ typedef struct pdx_pcg_part_desc {
     int32_t lower_window_index, upper_window_index;
     int32_t max_blocks;          /* cap on the cooperative grid (0 = auto); ranks sharing one GPU must fit together */
     int32_t timeout_ms;          /* a rank waiting longer than this for a peer gives up (0 = 10000) */
+    int32_t sell;                /* 0: CSR.  1: SELL-32 as in pdx_fem_explicit_step_sell - rowptr is slice_ptr
+                                    [ceil(n_local/32) + 1], col / aval / mval are slice-wise column-major, rows
+                                    padded with (col = any valid window index, val = 0) */
     const int32_t* rowptr;       /* n_local + 1 */
     const int32_t* col;          /* window-local */
     const float*   aval;         /* A = MASS + dt*STIFFNESS, rows of this rank */
@@ -312,15 +317,15 @@ int64_t pdx_pcg_part_workspace_bytes(int32_t max_window);
 int     pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_workspaces /* world */,
                             int32_t max_window, pdx_pcg_part** out);
 void    pdx_pcg_part_destroy(pdx_pcg_part* s);
-float*  pdx_pcg_part_x(pdx_pcg_part* s);        /* window, device */
-float*  pdx_pcg_part_rhs0(pdx_pcg_part* s);     /* window, device */
 int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s);
-/* Solve A x = b on the x window.  b: n_local values, or NULL to use b = MASS * rhs0 with the rhs0
- * window (all of it, ghosts included, valid on entry: fem_dist runs the ionic update over the window).
- * Every rank must call it with the same maxiter / toll / check_every.  info as pdx_pcg_solve, plus
- * flag bit2 = a peer did not answer within timeout_ms (fatal for the handle). */
-int     pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, int maxiter, double toll, int check_every,
-                           int32_t* info /* device, 4 words */, void* stream);
+/* Solve A x = b.  x: WINDOW (ghost_lo + n_local + ghost_hi floats): guess on entry - ghosts included,
+ * they must equal the owners' values - solution on exit, ghosts kept equal to the owners' values by the
+ * kernel.  b: n_local values, or NULL to use b = MASS * rhs0 with the rhs0 WINDOW (ghosts included:
+ * fem_dist runs the ionic update over the window).  Every rank must call it with the same maxiter /
+ * toll / check_every.  info as pdx_pcg_solve, plus flag bit2 = a peer did not answer within
+ * timeout_ms (fatal for the handle). */
+int     pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, const float* rhs0, float* x, int maxiter,
+                           double toll, int check_every, int32_t* info /* device, 4 words */, void* stream);
 
 /* ------------------------------------------------------------------ misc */
 int         pdx_version(void);

@@ -52,7 +52,7 @@ class PcgPartDesc(C.Structure):
     _fields_ = [('n_local', C.c_int32), ('ghost_lo', C.c_int32), ('ghost_hi', C.c_int32),
                 ('rank', C.c_int32), ('world', C.c_int32), ('send_lo', C.c_int32), ('send_hi', C.c_int32),
                 ('lower_window_index', C.c_int32), ('upper_window_index', C.c_int32),
-                ('max_blocks', C.c_int32), ('timeout_ms', C.c_int32),
+                ('max_blocks', C.c_int32), ('timeout_ms', C.c_int32), ('sell', C.c_int32),
                 ('rowptr', C.c_void_p), ('col', C.c_void_p), ('aval', C.c_void_p), ('mval', C.c_void_p),
                 ('minv', C.c_void_p)]
 
@@ -100,10 +100,8 @@ _SIGNATURES = {
     'pdx_pcg_part_workspace_bytes': (C.c_int64, [C.c_int32]),
     'pdx_pcg_part_create': (C.c_int, [C.POINTER(PcgPartDesc), C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
     'pdx_pcg_part_destroy': (None, [_P]),
-    'pdx_pcg_part_x': (_P, [_P]),
-    'pdx_pcg_part_rhs0': (_P, [_P]),
     'pdx_pcg_part_blocks': (C.c_int32, [_P]),
-    'pdx_pcg_part_solve': (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P]),
+    'pdx_pcg_part_solve': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -296,8 +296,8 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     if (res_ok && (want_resident || d.kernel == PDX_KERNEL_AUTO)) {
         const char* e = std::getenv("PDX_RESIDENT");            // A/B switch: PDX_RESIDENT=0 keeps AUTO on the per-step kernels
         p->resident_auto = want_resident || !(e && e[0] == '0');
-        if (check_cuda(cudaMalloc(&p->res_flags, sizeof(unsigned int) * (size_t)rg.ncta), "cudaMalloc(resident flags)") ||
-            check_cuda(cudaMemset(p->res_flags, 0, sizeof(unsigned int) * (size_t)rg.ncta), "clear resident flags") ||
+        if (check_cuda(cudaMalloc(&p->res_flags, sizeof(unsigned int) * PDX_RESIDENT_FLAG_STRIDE * (size_t)rg.ncta), "cudaMalloc(resident flags)") ||
+            check_cuda(cudaMemset(p->res_flags, 0, sizeof(unsigned int) * PDX_RESIDENT_FLAG_STRIDE * (size_t)rg.ncta), "clear resident flags") ||
             check_cuda(cudaMalloc(&p->res_halo, sizeof(float) * 4 * (size_t)rg.ncta * d.nz), "cudaMalloc(resident halo)")) {
             delete p;
             return 1;

@@ -9,8 +9,9 @@
 //   1. advances its first and last row (they are what the neighbours wait for),
 //   2. publishes them (2 x nz floats) to a global halo buffer and raises its step flag
 //      (st.release.gpu),
-//   3. advances its interior rows - which hides the flag latency of the neighbours, and
-//   4. at the start of the next step acquires the two neighbour flags and pulls their rows from L2.
+//   3. advances half of its interior rows - which hides the flag latency of the neighbours,
+//   4. acquires the two neighbour flags and issues the loads of their rows from L2,
+//   5. advances the other half while those loads are in flight, and stores them as next step's halo rows.
 // No grid-wide barrier, no HBM traffic between the first load and the final store.  The CTAs spin
 // on each other, so the kernel is launched cooperatively (co-residency guaranteed).
 //
@@ -25,6 +26,8 @@
 namespace pdx {
 namespace {
 
+constexpr int kFlagStride = PDX_RESIDENT_FLAG_STRIDE;   // one flag per 128-byte line
+
 struct ResArgs {
     const float* Uin;
     float* Uout;
@@ -33,7 +36,7 @@ struct ResArgs {
     int rows_per_cta;
     int nsteps;
     unsigned int base;          // flag value of "nothing published yet" for this launch
-    unsigned int* flags;        // [ncta]
+    unsigned int* flags;        // [ncta * kFlagStride]
     float* halo;                // [2][ncta][2][nz]
     float dt, coef;
     float hysq, hzsq, rhysq, rhzsq;
@@ -76,24 +79,27 @@ __global__ void __launch_bounds__(1024, 1) fd_resident_kernel(const __grid_const
     constexpr int NS = NStates<MODEL>::value;
     const int nz = a.nz, ny = a.ny;
     const int k = threadIdx.x;
+    const int waiter_hi = blockDim.x > 32 ? 32 : 0;
     const int c = blockIdx.x, ncta = gridDim.x;
-    const int j0 = c * a.rows_per_cta;
-    const int rows = min(a.rows_per_cta, ny - j0);
     const int R = a.rows_per_cta;
+    const int j0 = c * R;
+    const int rows = min(R, ny - j0);
     // shared memory: two U buffers of (R+2) rows (row 0 / rows+1 are the halos), then NS state arrays of R rows
     const int ustride = (R + 2) * nz;
-    float* Sbuf = smem + (size_t)2 * ustride;
+    const int sstride = R * nz;
+    float* const Sk = smem + 2 * ustride + k;          // this thread's column of state 0
     const bool active = k < nz;
+    const bool has_lo = c > 0, has_hi = c < ncta - 1;
 
     if (active) {
         for (int r = 0; r < rows; ++r) {
             const size_t g = (size_t)(j0 + r) * nz + k;
             smem[(r + 1) * nz + k] = a.Uin[g];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) Sbuf[((size_t)s * R + r) * nz + k] = a.st[s][g];
+            for (int q = 0; q < NS; ++q) Sk[q * sstride + r * nz] = a.st[q][g];
         }
-        if (j0 > 0) smem[k] = a.Uin[(size_t)(j0 - 1) * nz + k];
-        if (j0 + rows < ny) smem[(rows + 1) * nz + k] = a.Uin[(size_t)(j0 + rows) * nz + k];
+        if (has_lo) smem[k] = a.Uin[(size_t)(j0 - 1) * nz + k];
+        if (has_hi) smem[(rows + 1) * nz + k] = a.Uin[(size_t)(j0 + rows) * nz + k];
     }
     __syncthreads();
 
@@ -101,42 +107,37 @@ __global__ void __launch_bounds__(1024, 1) fd_resident_kernel(const __grid_const
     const int kc = min(max(k, 1), nz - 2);
     const int km = min(max(max(k - 1, 0), 1), nz - 2);
     const int kp = min(max(min(k + 1, nz - 1), 1), nz - 2);
+    const int mid = 1 + max(rows - 2, 0) / 2;            // interior rows [1, mid) before the halo prefetch, [mid, rows-1) after
 
     for (int s = 0; s < a.nsteps; ++s) {
-        float* cur = smem + (s & 1) * ustride;
+        const float* cur = smem + (s & 1) * ustride;
         float* nxt = smem + ((s & 1) ^ 1) * ustride;
-        if (s > 0) {
-            // rows published by the neighbours at step s-1
-            if (threadIdx.x == 0 && c > 0) wait_flag(a.flags + c - 1, a.base + s);
-            if (threadIdx.x == 32 && c < ncta - 1) wait_flag(a.flags + c + 1, a.base + s);
-            __syncthreads();
-            const float* hb = a.halo + (size_t)((s - 1) & 1) * ncta * 2 * nz;
-            if (active) {
-                if (c > 0) cur[k] = __ldcg(hb + ((size_t)(c - 1) * 2 + 1) * nz + k);
-                if (c < ncta - 1) cur[(rows + 1) * nz + k] = __ldcg(hb + ((size_t)(c + 1) * 2 + 0) * nz + k);
-            }
-            __syncthreads();
-        }
+        const bool more = s + 1 < a.nsteps;
         auto update = [&](int r) {
             const int jg = j0 + r;
-            const int jc = min(max(jg, 1), ny - 2) - j0 + 1;
-            const int jm = min(max(max(jg - 1, 0), 1), ny - 2) - j0 + 1;
-            const int jp = min(max(min(jg + 1, ny - 1), 1), ny - 2) - j0 + 1;
-            const float cval = cur[jc * nz + kc];
-            float lap = lap_axis<MATH>(cur[jm * nz + kc], cval, cur[jp * nz + kc], a.hysq, a.rhysq);
-            lap = madd<MATH>(lap, lap_axis<MATH>(cur[jc * nz + km], cval, cur[jc * nz + kp], a.hzsq, a.rhzsq));
+            const int oraw = (r + 1) * nz;               // this node's own row in the buffer
+            int oc = oraw, om = oraw - nz, op = oraw + nz;
+            if (jg < 2 || jg > ny - 3) {                 // rows touched by the boundary rule
+                oc = (min(max(jg, 1), ny - 2) - j0 + 1) * nz;
+                om = (min(max(max(jg - 1, 0), 1), ny - 2) - j0 + 1) * nz;
+                op = (min(max(min(jg + 1, ny - 1), 1), ny - 2) - j0 + 1) * nz;
+            }
+            const float cval = cur[oc + kc];
+            float lap = lap_axis<MATH>(cur[om + kc], cval, cur[op + kc], a.hysq, a.rhysq);
+            lap = madd<MATH>(lap, lap_axis<MATH>(cur[oc + km], cval, cur[oc + kp], a.hzsq, a.rhzsq));
             float u1 = cval;
             if (MODEL != PDX_MODEL_NONE) {
                 float st[PDX_MAX_STATES];
+                float* sp = Sk + r * nz;
 #pragma unroll
-                for (int q = 0; q < NS; ++q) st[q] = Sbuf[((size_t)q * R + r) * nz + k];
-                const float dU = ionic_update<MODEL, MATH>(cur[(r + 1) * nz + k], st, a.mp);    // raw U, not U0
+                for (int q = 0; q < NS; ++q) st[q] = sp[q * sstride];
+                const float dU = ionic_update<MODEL, MATH>(cur[oraw + k], st, a.mp);    // raw U, not U0
 #pragma unroll
-                for (int q = 0; q < NS; ++q) Sbuf[((size_t)q * R + r) * nz + k] = st[q];
+                for (int q = 0; q < NS; ++q) sp[q * sstride] = st[q];
                 u1 = madd<MATH>(u1, mmul<MATH>(a.dt, dU));
             }
             const float un = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
-            nxt[(r + 1) * nz + k] = un;
+            nxt[oraw + k] = un;
             return un;
         };
         // 1. the rows the neighbours wait for
@@ -146,21 +147,41 @@ __global__ void __launch_bounds__(1024, 1) fd_resident_kernel(const __grid_const
             last = rows > 1 ? update(rows - 1) : first;
         }
         // 2. publish them
-        if (s + 1 < a.nsteps) {
-            float* hb = a.halo + (size_t)(s & 1) * ncta * 2 * nz;
+        float* hb = a.halo + (size_t)(s & 1) * ncta * 2 * nz;
+        if (more) {
             if (active) {
-                __stcg(hb + ((size_t)c * 2 + 0) * nz + k, first);
-                __stcg(hb + ((size_t)c * 2 + 1) * nz + k, last);
+                __stcg(hb + (c * 2 + 0) * nz + k, first);
+                __stcg(hb + (c * 2 + 1) * nz + k, last);
             }
             __syncthreads();
             if (threadIdx.x == 0) {
                 __threadfence();
-                st_release_gpu_u32(a.flags + c, a.base + s + 1);
+                st_release_gpu_u32(a.flags + c * kFlagStride, a.base + s + 1);
             }
         }
-        // 3. interior rows
+        // 3. first half of the interior rows: covers the flight time of the neighbours' flags
         if (active)
-            for (int r = 1; r < rows - 1; ++r) update(r);
+            for (int r = 1; r < mid; ++r) update(r);
+        // 4. the neighbours' rows of this step: two threads acquire the flags (more pollers only queue up on the
+        //    L2 slice that holds them), the loads stay in flight during 5.
+        float h_lo = 0.0f, h_hi = 0.0f;
+        if (more) {
+            if (threadIdx.x == 0 && has_lo) wait_flag(a.flags + (c - 1) * kFlagStride, a.base + s + 1);
+            if (threadIdx.x == waiter_hi && has_hi) wait_flag(a.flags + (c + 1) * kFlagStride, a.base + s + 1);
+            __syncthreads();
+            if (active) {
+                if (has_lo) h_lo = __ldcg(hb + ((c - 1) * 2 + 1) * nz + k);
+                if (has_hi) h_hi = __ldcg(hb + ((c + 1) * 2 + 0) * nz + k);
+            }
+        }
+        // 5. second half of the interior rows
+        if (active)
+            for (int r = mid; r < rows - 1; ++r) update(r);
+        // 6. halo rows of the next step's input
+        if (more && active) {
+            if (has_lo) nxt[k] = h_lo;
+            if (has_hi) nxt[(rows + 1) * nz + k] = h_hi;
+        }
         __syncthreads();
     }
 
@@ -170,7 +191,7 @@ __global__ void __launch_bounds__(1024, 1) fd_resident_kernel(const __grid_const
             const size_t g = (size_t)(j0 + r) * nz + k;
             a.Uout[g] = fin[(r + 1) * nz + k];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) a.st[s][g] = Sbuf[((size_t)s * R + r) * nz + k];
+            for (int q = 0; q < NS; ++q) a.st[q][g] = Sk[q * sstride + r * nz];
         }
     }
 }

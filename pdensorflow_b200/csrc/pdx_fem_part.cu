@@ -158,38 +158,71 @@ __device__ __forceinline__ bool all_reduce(const PartArgs& a, cg::grid_group& gr
     return ok;
 }
 
+// Row products of the kernel's SpMV phases: f(row, A_row . xa, M_row . xm) is called once per owned row
+// by the lane that owns it (mv == nullptr: the second product is skipped and 0 is passed).
+//  G > 0: CSR, G lanes per row.   G == 0: SELL-32 (a.rowptr = slice_ptr): a warp per 32-row slice, one
+//  thread per row, column-major inside the slice so that every col/val access is a coalesced 128-byte load.
+template <int G, class F>
+__device__ __forceinline__ void rows_dot(const PartArgs& a, const float* xa, const float* mv, const float* xm, F&& f) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    if constexpr (G == 0) {
+        const int lane = threadIdx.x & 31;
+        const int nsl = (a.n + 31) >> 5;
+        for (int sl = tid >> 5; sl < nsl; sl += nthreads >> 5) {
+            const int beg = a.rowptr[sl], end = a.rowptr[sl + 1];
+            float acc = 0.0f, accm = 0.0f;
+            if (mv) {
+#pragma unroll 2
+                for (int k = beg + lane; k < end; k += 32) {
+                    const int c = a.col[k];
+                    acc = fmaf(a.aval[k], __ldcg(xa + c), acc);
+                    accm = fmaf(mv[k], __ldcg(xm + c), accm);
+                }
+            } else {
+#pragma unroll 4
+                for (int k = beg + lane; k < end; k += 32) acc = fmaf(a.aval[k], __ldcg(xa + a.col[k]), acc);
+            }
+            const int row = sl * 32 + lane;
+            if (row < a.n) f(row, acc, accm);
+        }
+    } else {
+        const int gid = tid / G, sub = threadIdx.x % G, ngroups = nthreads / G;
+        const int nround = (a.n + ngroups - 1) / ngroups * ngroups;     // keep groups converged for the shuffles
+        for (int row = gid; row < nround; row += ngroups) {
+            const bool valid = row < a.n;
+            const int beg = valid ? a.rowptr[row] : 0, end = valid ? a.rowptr[row + 1] : 0;
+            const float acc = row_dot<(G > 0 ? G : 1)>(a.col, a.aval, xa, beg, end, sub, true);
+            float accm = 0.0f;
+            if (mv) accm = row_dot<(G > 0 ? G : 1)>(a.col, mv, xm, beg, end, sub, true);   // uniform branch
+            if (valid && sub == 0) f(row, acc, accm);
+        }
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(256) pcg_part_kernel(const __grid_constant__ PartArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[33];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
-    const int gid = tid / G, sub = threadIdx.x % G, ngroups = nthreads / G;
-    const int nround = (a.n + ngroups - 1) / ngroups * ngroups;
     const int glo = a.glo;
     const int hi_first = a.n - a.send_hi;          // first row the upper neighbour holds as a ghost
     unsigned int epoch = *((volatile unsigned int*)&a.comm->epoch);
 
     // b = M rhs0 (optional) ; r = b - A x ; z = Minv r ; p = z ; rz = r.z      (conjgrad.py:191-203)
     float loc_rz = 0.0f, loc_rr = 0.0f;
-    for (int row = gid; row < nround; row += ngroups) {
-        const bool valid = row < a.n;
-        const int beg = valid ? a.rowptr[row] : 0, end = valid ? a.rowptr[row + 1] : 0;
-        const float ax = row_dot<G>(a.col, a.aval, a.x, beg, end, sub, true);
-        float bv = 0.0f;
-        if (a.mval) bv = row_dot<G>(a.col, a.mval, a.rhs0, beg, end, sub, true);   // uniform branch
-        if (valid && sub == 0) {
-            if (!a.mval) bv = a.b[row];
-            const float r = __fsub_rn(bv, ax);
-            const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
-            __stcg(a.r + row, r);
-            __stcg(a.p + glo + row, z);
-            if (row < a.send_lo) a.peer_lo_p[row] = z;                 // the neighbours' ghost p = z
-            if (row >= hi_first) a.peer_hi_p[row - hi_first] = z;
-            loc_rz = fmaf(r, z, loc_rz);
-            loc_rr = fmaf(r, r, loc_rr);
-        }
-    }
+    rows_dot<G>(a, a.x, a.mval, a.rhs0, [&](int row, float ax, float bm) {
+        const float bv = a.mval ? bm : a.b[row];
+        const float r = __fsub_rn(bv, ax);
+        const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
+        __stcg(a.r + row, r);
+        __stcg(a.p + glo + row, z);
+        if (row < a.send_lo) a.peer_lo_p[row] = z;                 // the neighbours' ghost p = z
+        if (row >= hi_first) a.peer_hi_p[row - hi_first] = z;
+        loc_rz = fmaf(r, z, loc_rz);
+        loc_rr = fmaf(r, r, loc_rr);
+    });
     float rz, res;
     bool ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rz, &res);
 
@@ -198,15 +231,10 @@ __global__ void __launch_bounds__(256) pcg_part_kernel(const __grid_constant__ P
         niters = k;
         // q = A p ; pq = p.q
         float loc_pq = 0.0f;
-        for (int row = gid; row < nround; row += ngroups) {
-            const bool valid = row < a.n;
-            const float ap = row_dot<G>(a.col, a.aval, a.p, valid ? a.rowptr[row] : 0, valid ? a.rowptr[row + 1] : 0,
-                                        sub, true);
-            if (valid && sub == 0) {
-                __stcg(a.q + row, ap);
-                loc_pq = fmaf(__ldcg(a.p + glo + row), ap, loc_pq);
-            }
-        }
+        rows_dot<G>(a, a.p, nullptr, nullptr, [&](int row, float ap, float) {
+            __stcg(a.q + row, ap);
+            loc_pq = fmaf(__ldcg(a.p + glo + row), ap, loc_pq);
+        });
         float pq, unused;
         ok = all_reduce<1>(a, grid, epoch, sh, loc_pq, 0.0f, &pq, &unused);
         if (!ok) break;
@@ -283,7 +311,7 @@ struct pdx_pcg_part {
     int64_t nnz;
     int G, nblocks;
     char* ws;               // own workspace
-    float *x, *p, *zg, *rhs0;
+    float *p, *zg;          // windows inside the workspace (written by the neighbours)
     float* work;            // r, q
     float* part;
     PartArgs base;
@@ -293,7 +321,7 @@ extern "C" {
 
 int64_t pdx_pcg_part_workspace_bytes(int32_t max_window) {
     if (max_window <= 0) return 0;
-    return (int64_t)(COMM_BYTES + 4 * align_up(sizeof(float) * (size_t)max_window, 256));
+    return (int64_t)(COMM_BYTES + 2 * align_up(sizeof(float) * (size_t)max_window, 256));
 }
 
 int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_t max_window, pdx_pcg_part** out) {
@@ -324,16 +352,18 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     s->d = *d;
     s->window = window;
     int32_t last = 0;
-    if (check_cuda(cudaMemcpy(&last, d->rowptr + d->n_local, sizeof(int32_t), cudaMemcpyDeviceToHost), "read nnz")) {
+    const int nptr = d->sell ? (d->n_local + 31) / 32 : d->n_local;
+    if (check_cuda(cudaMemcpy(&last, d->rowptr + nptr, sizeof(int32_t), cudaMemcpyDeviceToHost), "read nnz")) {
         delete s; return 1;
     }
     s->nnz = last;
-    s->G = pick_group(d->n_local, s->nnz);
+    s->G = d->sell ? 0 : pick_group(d->n_local, s->nnz);
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e;
     switch (s->G) {
+        case 0:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<0>, 256, 0); break;
         case 4:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<4>, 256, 0); break;
         case 8:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<8>, 256, 0); break;
         case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<16>, 256, 0); break;
@@ -343,10 +373,13 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
         if (per_sm < 1) set_error("pcg_part kernel cannot be resident");
         delete s; return 1;
     }
-    long long want = ((long long)d->n_local * s->G + 255) / 256;
-    long long cap = (long long)sms * (per_sm > 4 ? 4 : per_sm);
+    const int lanes = s->G > 0 ? s->G : 1;
+    long long want = ((long long)d->n_local * lanes + 255) / 256;
+    // big systems are bandwidth bound: fill the SMs; small ones are latency bound: one block per SM keeps the
+    // grid barrier cheap
+    long long cap = (long long)sms * per_sm;
     long long nb = want < cap ? want : cap;
-    if (nb > sms && (long long)d->n_local * s->G <= (long long)sms * 256 * 8) nb = sms;
+    if (nb > sms && (long long)d->n_local * lanes <= (long long)sms * 256 * 8) nb = sms;
     if (d->max_blocks > 0 && nb > d->max_blocks) nb = d->max_blocks;
     if (nb < 1) nb = 1;
     s->nblocks = (int)nb;
@@ -354,8 +387,6 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     s->ws = (char*)peer_ws[d->rank];
     s->p    = (float*)(s->ws + COMM_BYTES);
     s->zg   = (float*)(s->ws + COMM_BYTES + vec);
-    s->x    = (float*)(s->ws + COMM_BYTES + 2 * vec);
-    s->rhs0 = (float*)(s->ws + COMM_BYTES + 3 * vec);
     if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 2 * (size_t)d->n_local), "cudaMalloc(pcg_part work)")) { delete s; return 1; }
     if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 2 * (size_t)s->nblocks), "cudaMalloc(pcg_part partials)")) {
         cudaFree(s->work); delete s; return 1;
@@ -368,7 +399,7 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     a = PartArgs{};
     a.n = d->n_local; a.glo = d->ghost_lo; a.ghi = d->ghost_hi;
     a.rowptr = d->rowptr; a.col = d->col; a.aval = d->aval; a.mval = d->mval; a.minv = d->minv;
-    a.x = s->x; a.p = s->p; a.zg = s->zg; a.rhs0 = s->rhs0;
+    a.p = s->p; a.zg = s->zg;
     a.r = s->work; a.q = s->work + d->n_local;
     a.part = s->part;
     a.comm = (Comm*)s->ws;
@@ -397,16 +428,19 @@ void pdx_pcg_part_destroy(pdx_pcg_part* s) {
     delete s;
 }
 
-float* pdx_pcg_part_x(pdx_pcg_part* s) { return s ? s->x : nullptr; }
-float* pdx_pcg_part_rhs0(pdx_pcg_part* s) { return s ? s->rhs0 : nullptr; }
 int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s) { return s ? s->nblocks : 0; }
 
-int pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, int maxiter, double toll, int check_every, int32_t* info,
-                       void* stream) {
-    if (!s || maxiter < 0) { set_error("pdx_pcg_part_solve: bad arguments"); return 1; }
-    if (!b && !s->d.mval) { set_error("pdx_pcg_part_solve: b is NULL and the handle has no mass matrix"); return 1; }
+int pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, const float* rhs0, float* x, int maxiter, double toll,
+                       int check_every, int32_t* info, void* stream) {
+    if (!s || !x || maxiter < 0) { set_error("pdx_pcg_part_solve: bad arguments"); return 1; }
+    if (!b && !(s->d.mval && rhs0)) {
+        set_error("pdx_pcg_part_solve: without b the handle needs a mass matrix and the call an rhs0 window");
+        return 1;
+    }
     PartArgs a = s->base;
     a.b = b;
+    a.x = x;
+    a.rhs0 = rhs0;
     if (b) a.mval = nullptr;
     a.maxiter = maxiter;
     a.check_every = check_every > 0 ? check_every : 1;
@@ -415,6 +449,7 @@ int pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, int maxiter, double toll
     void* args[] = {&a};
     const void* fn;
     switch (s->G) {
+        case 0:  fn = (const void*)pcg_part_kernel<0>; break;
         case 4:  fn = (const void*)pcg_part_kernel<4>; break;
         case 8:  fn = (const void*)pcg_part_kernel<8>; break;
         case 16: fn = (const void*)pcg_part_kernel<16>; break;

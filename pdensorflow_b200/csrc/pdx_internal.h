@@ -86,6 +86,7 @@ void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* b
 int  fd_tma_auto_chunk(const pdx_fd_desc& d);
 
 // SM-resident multi-step kernel for 2-D grids (pdx_fd_resident.cu)
+#define PDX_RESIDENT_FLAG_STRIDE 32
 struct ResidentGeom {
     int rows_per_cta, ncta, threads;
     size_t smem_bytes;

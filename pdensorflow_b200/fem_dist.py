@@ -236,7 +236,7 @@ class PartitionedSemiImplicitFEM:
 
     def __init__(self, n_global, rowptr, col, mval, kval, dt, model='fenton4v', params=None, rank=0, world=1,
                  group=None, math='fast', device=None, maxiter=100, toll=1e-5, check_every=5, max_blocks=0,
-                 timeout_ms=0, stream=None, connect=True):
+                 timeout_ms=0, stream=None, connect=True, layout='sell'):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != 'cuda':
             raise L.PdxError('PartitionedSemiImplicitFEM needs a CUDA device: there is no CPU path')
@@ -268,6 +268,9 @@ class PartitionedSemiImplicitFEM:
         p = (L.default_params(self.model_id) if params is None else list(params)) if self.model_id != L.MODEL_NONE else []
         self._params = (C.c_float * L.MAX_PARAMS)(*p)
         self.stream = stream
+        if layout not in ('sell', 'csr'):
+            raise ValueError("layout must be 'sell' or 'csr'")
+        self.layout = layout
         self._h = None
         self._symm = None
         self.nsteps_done = 0
@@ -316,10 +319,17 @@ class PartitionedSemiImplicitFEM:
 
     def _attach(self, peer_ptrs):
         dev = self.device
-        self.rowptr = torch.from_numpy(self._rowptr_h).to(dev)
-        self.col = torch.from_numpy((self._col_h - (self.lo - self.glo)).astype(np.int32)).to(dev)   # window-local
-        self.aval = torch.from_numpy(self._aval_h).to(dev)
-        self.mval = torch.from_numpy(self._mval_h).to(dev)
+        rowptr, col = self._rowptr_h, (self._col_h - (self.lo - self.glo)).astype(np.int32)   # window-local columns
+        aval, mval = self._aval_h, self._mval_h
+        if self.layout == 'sell':       # SELL-32: thread per row, coalesced matrix loads (as the explicit step)
+            sp, scol, aval = csr_to_sell32(rowptr, col, aval, self.glo)
+            _, _, mval = csr_to_sell32(rowptr, col, mval, self.glo)
+            self.padding = scol.shape[0] / max(int(rowptr[-1]), 1)
+            rowptr, col = sp, scol
+        self.rowptr = torch.from_numpy(rowptr).to(dev)
+        self.col = torch.from_numpy(col).to(dev)
+        self.aval = torch.from_numpy(np.ascontiguousarray(aval)).to(dev)
+        self.mval = torch.from_numpy(np.ascontiguousarray(mval)).to(dev)
         self.minv = torch.from_numpy(self._minv_h).to(dev)
         d = L.PcgPartDesc()
         d.n_local, d.ghost_lo, d.ghost_hi = self.nloc, self.glo, self.ghi
@@ -327,21 +337,16 @@ class PartitionedSemiImplicitFEM:
         d.send_lo, d.send_hi = self.plan['send_lo'], self.plan['send_hi']
         d.lower_window_index, d.upper_window_index = self.plan['lower_window_index'], self.plan['upper_window_index']
         d.max_blocks, d.timeout_ms = self.max_blocks, self.timeout_ms
+        d.sell = 1 if self.layout == 'sell' else 0
         d.rowptr, d.col, d.aval = self.rowptr.data_ptr(), self.col.data_ptr(), self.aval.data_ptr()
         d.mval, d.minv = self.mval.data_ptr(), self.minv.data_ptr()
         arr = (C.c_void_p * self.world)(*peer_ptrs)
         h = C.c_void_p()
         L.check(L.lib().pdx_pcg_part_create(C.byref(d), arr, self.max_window, C.byref(h)))
         self._h = h
-        base = self.ws.data_ptr()
-
-        def view(ptr):
-            off = int(ptr) - base
-            return self.ws[off:off + 4 * self.window].view(torch.float32)
-
-        self.U = view(L.lib().pdx_pcg_part_x(h))             # potential window: guess in, solution out
-        self.rhs0 = view(L.lib().pdx_pcg_part_rhs0(h))
-        self.U.fill_(-80.0 if self.model_id != L.MODEL_NONE else 0.0)
+        # potential window (guess in, solution out) and RHS0 window: ordinary device arrays, no peer touches them
+        self.U = torch.full((self.window,), -80.0 if self.model_id != L.MODEL_NONE else 0.0, dtype=torch.float32, device=dev)
+        self.rhs0 = torch.empty_like(self.U)
         self.states = [torch.full((self.window,), v, dtype=torch.float32, device=dev) for v in STATE_INIT[self.model_id]]
         self._states_arr = L.ptr_array(self.states)
         self.info = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -384,8 +389,8 @@ class PartitionedSemiImplicitFEM:
     # ---- stepping ---------------------------------------------------------------------------
     def solve(self, b=None):
         """A x = b on the potential window (b: owned rows; None: b = MASS * rhs0 window)."""
-        L.check(L.lib().pdx_pcg_part_solve(self._h, L.ptr(b), self.maxiter, self.toll, self.check_every,
-                                           L.ptr(self.info), L.stream_ptr(self.stream)))
+        L.check(L.lib().pdx_pcg_part_solve(self._h, L.ptr(b), L.ptr(self.rhs0), L.ptr(self.U), self.maxiter, self.toll,
+                                           self.check_every, L.ptr(self.info), L.stream_ptr(self.stream)))
 
     def step(self, nsteps=1, I0=None):
         """nsteps semi-implicit time steps; I0: window-length forcing (window_of(global I0)) or None."""
@@ -403,5 +408,6 @@ class PartitionedSemiImplicitFEM:
                 # RHS0 = U + dt*(differentiate(U) + I0) over the whole window   (monodomainSolver.py:100-103)
                 L.check(lib.pdx_ionic_step(self.model_id, self.math_id, self._params, None, self.window, L.ptr(self.U),
                                            self._states_arr, None, dt32, L.ptr(I0), L.ptr(self.rhs0), sp))
-            L.check(lib.pdx_pcg_part_solve(self._h, None, self.maxiter, self.toll, self.check_every, L.ptr(self.info), sp))
+            L.check(lib.pdx_pcg_part_solve(self._h, None, L.ptr(self.rhs0), L.ptr(self.U), self.maxiter, self.toll,
+                                           self.check_every, L.ptr(self.info), sp))
         self.nsteps_done += nsteps

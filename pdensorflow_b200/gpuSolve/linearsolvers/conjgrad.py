@@ -4,7 +4,10 @@ The reference runs ~12 eager TensorFlow ops per CG iteration and synchronises wi
 ``check_every`` iterations (conjgrad.py:287-301).  Here the whole solve - r = b - A x, the Jacobi
 scaling, every SpMV / dot / axpy and the batched convergence test with its NaN/Inf guard - is ONE
 persistent cooperative kernel (pdx_pcg_solve); the iteration count and ||r||^2 come back through a
-4-word device record that is only read when somebody asks for it.
+4-word device record that is only read when somebody asks for it.  Small systems (config 1: 63 001 rows,
+L2 resident, latency bound) use the CSR kernel with a few lanes per row; above ``SELL_MIN_ROWS`` rows the solve
+is bandwidth bound and uses SELL-32 storage (thread per row, coalesced matrix loads) through the single-rank
+form of the partitioned kernel (pdx_pcg_part_solve, world = 1).
 """
 import ctypes as C
 
@@ -15,6 +18,9 @@ from .abstract_precond import AbstractPrecond
 from .. import _backend as B
 from ... import _lib as L
 from ..matrices.globalMatrices import CSRMatrix
+
+
+SELL_MIN_ROWS = 100000
 
 
 class ConjGrad:
@@ -37,6 +43,7 @@ class ConjGrad:
                 self._Precond = config['precond']
         self._handle = None
         self._handle_key = None
+        self._part = None                 # (handle, workspace, sell arrays) of the large-system path
         self._info = None
         self._info_host = None
 
@@ -47,9 +54,12 @@ class ConjGrad:
         try:
             if self._handle is not None:
                 L.lib().pdx_pcg_destroy(self._handle)
+            if self._part is not None:
+                L.lib().pdx_pcg_part_destroy(self._part[0])
         except Exception:
             pass
         self._handle = None
+        self._part = None
 
     # ---- configuration ----
     def set_precond(self, prcnd):
@@ -141,27 +151,49 @@ class ConjGrad:
                 raise L.PdxError('ConjGrad: only diagonal (Jacobi) preconditioners are supported on the device')
             minv = self._Precond.inverse_diagonal()
         key = (id(self._A), None if minv is None else minv.data_ptr())
-        if self._handle is None or self._handle_key != key:
+        if (self._handle is None and self._part is None) or self._handle_key != key:
             self._release()
             rp, ci, va = self._A.device_arrays()
             h = C.c_void_p()
-            L.check(L.lib().pdx_pcg_create(self._A.n, L.ptr(rp), L.ptr(ci), L.ptr(va), L.ptr(minv), C.byref(h)))
-            self._handle, self._handle_key, self._minv = h, key, minv
+            if self._A.n >= SELL_MIN_ROWS:
+                from ...fem_dist import csr_to_sell32
+                sp, scol, sval = csr_to_sell32(self._A.rowptr, self._A.col, self._A.val)
+                dev = rp.device
+                arrs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sp, scol, sval)]
+                ws = torch.zeros(int(L.lib().pdx_pcg_part_workspace_bytes(self._A.n)), dtype=torch.uint8, device=dev)
+                d = L.PcgPartDesc()
+                d.n_local, d.rank, d.world, d.sell = self._A.n, 0, 1, 1
+                d.lower_window_index = d.upper_window_index = -1
+                d.rowptr, d.col, d.aval = (a.data_ptr() for a in arrs)
+                d.minv = None if minv is None else minv.data_ptr()
+                peers = (C.c_void_p * 1)(ws.data_ptr())
+                L.check(L.lib().pdx_pcg_part_create(C.byref(d), peers, self._A.n, C.byref(h)))
+                self._part = (h, ws, arrs)
+            else:
+                L.check(L.lib().pdx_pcg_create(self._A.n, L.ptr(rp), L.ptr(ci), L.ptr(va), L.ptr(minv), C.byref(h)))
+                self._handle = h
+            self._handle_key, self._minv = key, minv
             self._info = torch.zeros(4, dtype=torch.int32, device=rp.device)
+
+    def _launch(self, b, x):
+        if self._part is not None:
+            L.check(L.lib().pdx_pcg_part_solve(self._part[0], L.ptr(b), None, L.ptr(x), int(self._maxiter), float(self._toll),
+                                               int(self._check_every), L.ptr(self._info), L.stream_ptr()))
+        else:
+            L.check(L.lib().pdx_pcg_solve(self._handle, L.ptr(b), L.ptr(x), int(self._maxiter), float(self._toll),
+                                          int(self._check_every), L.ptr(self._info), L.stream_ptr()))
 
     def solve(self):
         """Solve A X = RHS from the initial guess held in X (in place)."""
         self._ensure_handle()
         if self._X is None or self._RHS is None:
             raise L.PdxError('ConjGrad: set_X0() and set_RHS() must be called before solve()')
-        L.check(L.lib().pdx_pcg_solve(self._handle, L.ptr(self._RHS), L.ptr(self._X), int(self._maxiter),
-                                      float(self._toll), int(self._check_every), L.ptr(self._info), L.stream_ptr()))
+        self._launch(self._RHS, self._X)
         if self._verbose:
             self.summary()
 
     def solve_inplace(self, b, x):
         """Zero-copy variant used by the solvers: A x = b, x holds the guess and receives the solution."""
         self._ensure_handle()
-        L.check(L.lib().pdx_pcg_solve(self._handle, L.ptr(b), L.ptr(x), int(self._maxiter), float(self._toll),
-                                      int(self._check_every), L.ptr(self._info), L.stream_ptr()))
+        self._launch(b, x)
         self._X = x

@@ -48,7 +48,8 @@ def _make(rank=0, world=1, **kw):
 def test_one_rank_solve_matches_single_gpu_pcg(cuda):
     from pdensorflow_b200 import _lib as L
     n = DIMS[0] * DIMS[1] * DIMS[2]
-    fem = _make(model='none', maxiter=400, toll=1e-6)
+    fem = _make(model='none', maxiter=400, toll=1e-6, layout='csr')
+    sell = _make(model='none', maxiter=400, toll=1e-6, layout='sell')
     rng = np.random.default_rng(3)
     xs = rng.standard_normal(n).astype(np.float32)
     b = torch.from_numpy(xs).cuda()
@@ -65,6 +66,10 @@ def test_one_rank_solve_matches_single_gpu_pcg(cuda):
     L.lib().pdx_pcg_destroy(h)
     assert flags == 0 and abs(it - int(info[0].item())) <= 5 and res < 1e-12
     assert rel_l2(fem.owned_U().cpu().numpy(), x1.cpu().numpy()) <= 1e-5
+    sell.U.zero_()
+    sell.solve(b)                                   # same system, SELL-32 storage
+    assert abs(sell.last_solve()[0] - it) <= 5 and sell.padding < 1.5     # tiny mesh: boundary rows are short
+    assert rel_l2(sell.owned_U().cpu().numpy(), x1.cpu().numpy()) <= 1e-5
     # and it solves the system
     import scipy.sparse as sp
     A = sp.csr_matrix((fem.aval.cpu().numpy().astype(np.float64), fem.col.cpu().numpy(), fem.rowptr.cpu().numpy()), shape=(n, n))
@@ -91,10 +96,11 @@ def _oracle_steps(nsteps):
     return U, its
 
 
-def test_one_rank_steps_match_oracle(cuda):
+@pytest.mark.parametrize('layout', ['sell', 'csr'])
+def test_one_rank_steps_match_oracle(cuda, layout):
     nsteps = 25
     Uo, its = _oracle_steps(nsteps)
-    fem = _make(math='exact')
+    fem = _make(math='exact', layout=layout)
     fem.set_global_U(_initial())
     got_its = []
     for _ in range(nsteps):
@@ -106,19 +112,19 @@ def test_one_rank_steps_match_oracle(cuda):
     assert _same_iterations(got_its, its), (got_its, its)
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_ranks_sharing_one_gpu_match_one_rank(cuda, world):
+@pytest.mark.parametrize('world,layout', [(2, 'sell'), (3, 'sell'), (2, 'csr')])
+def test_ranks_sharing_one_gpu_match_one_rank(cuda, world, layout):
     from pdensorflow_b200.fem_dist import PartitionedSemiImplicitFEM
     nsteps = 20
-    ref = _make(math='exact')
+    ref = _make(math='exact', layout=layout)
     ref.set_global_U(_initial())
     ref_its = []
     for _ in range(nsteps):
         ref.step(1)
         ref_its.append(ref.last_solve()[0])
     Uref, Vref = ref.owned_U().cpu().numpy(), ref.owned_state(0).cpu().numpy()
-    ranks = [_make(r, world, math='exact', connect=False, max_blocks=16, timeout_ms=5000, stream=torch.cuda.Stream())
-             for r in range(world)]
+    ranks = [_make(r, world, math='exact', connect=False, max_blocks=16, timeout_ms=5000, stream=torch.cuda.Stream(),
+                   layout=layout) for r in range(world)]
     PartitionedSemiImplicitFEM.connect_local(ranks)
     for f in ranks:
         assert (f.glo > 0) == (f.rank > 0) and (f.ghi > 0) == (f.rank < world - 1)
@@ -207,3 +213,37 @@ def test_two_gpus_match_one_rank(cuda):
     for rank, lo, U, its in got:
         assert _same_iterations(its, ref_its), (its, ref_its)
         assert rel_l2(U, Uref[lo:lo + U.shape[0]]) <= TOL_CG
+
+
+def test_conjgrad_takes_the_sell_path_for_large_systems(cuda):
+    """gpuSolve.linearsolvers.ConjGrad above SELL_MIN_ROWS rows = the single-rank form of the partitioned kernel on
+    SELL-32 storage: test_conjgrad.py:117-162 (seeded gold solution, zero guess) on a 48^3 tetrahedral operator."""
+    from oracle import fem as ofem
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    from pdensorflow_b200.gpuSolve.linearsolvers import ConjGrad, JacobiPrecond
+    from pdensorflow_b200.gpuSolve.linearsolvers.conjgrad import SELL_MIN_ROWS
+    from pdensorflow_b200.gpuSolve.matrices import CSRMatrix
+    m = 48
+    n = m ** 3
+    assert n >= SELL_MIN_ROWS
+    rp, ci, kv, ml, mv = structured_tet_operator(m, m, m, H, 1.0, consistent_mass=True)     # sigma = 1: a real Laplacian part
+    val = ofem.csr_axpby(mv, 1.0, kv, DT)
+    gold = np.random.default_rng(0).standard_normal(n).astype(np.float32)
+    b = ofem.spmv(rp, ci, val, gold)
+    M = CSRMatrix(rp, ci, val, n)
+    pc = JacobiPrecond()
+    pc.build_preconditioner(*M.coo(), n)
+    toll = 1e-6 * float(np.linalg.norm(b))
+    cg = ConjGrad({'maxiter': 2000, 'toll': toll, 'precond': pc})
+    cg.set_matrix(M)
+    cg.set_X0(torch.zeros(n, 1, device='cuda'))
+    cg.set_RHS(torch.from_numpy(b[:, None]).cuda())
+    cg.solve()
+    assert cg._part is not None and cg._handle is None
+    x = cg.X().cpu().numpy().ravel()
+    assert cg.niters() < 2000 and cg.niters() % 5 == 0
+    assert np.linalg.norm(b - ofem.spmv(rp, ci, val, x)) / np.linalg.norm(b) < 1e-4
+    minv = ofem.jacobi(rp, ci, val, n)
+    xo, nit_o, _ = ofem.pcg(rp, ci, val, minv, b, np.zeros(n, np.float32), 2000, toll)
+    assert abs(cg.niters() - nit_o) <= 5
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-4
