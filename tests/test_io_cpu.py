@@ -1,0 +1,136 @@
+"""Result writers on the stepping loop against fixtures written by the REFERENCE'S OWN
+writers (tests/golden/make_io_golden.py -> ref_io.npz): IGB files byte for byte, ResultWriter arrays, chunk
+counts; plus the reference's round-trip unit test (Tests/CICD/unit/test_igb_roundtrip.py) transcribed."""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, 'golden', 'ref_io.npz'))
+
+
+@pytest.fixture()
+def in_tmp(tmp_path):
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    yield tmp_path
+    os.chdir(cwd)
+
+
+def test_igb_files_are_byte_identical_to_the_reference(in_tmp):
+    from pdensorflow_b200.gpuSolve.IO.writers import IGBWriter
+    fr = G['igb_a_frames']
+    w = IGBWriter({'fname': 'a.igb', 'Tend': 600.0, 'nt': fr.shape[0], 'nx': fr.shape[1], 'every_N': 3})
+    for f in fr:
+        w.imshow(f)
+    w.wait()
+    assert open('a.igb', 'rb').read() == G['igb_a_bytes'].tobytes()
+    fr = G['igb_b_frames']
+    w = IGBWriter({'fname': 'sub/b', 'nt': fr.shape[0], 'nx': 12, 'ny': 5, 'nz': 3, 'org_t': 2.5, 'dim_t': 30.0,
+                   'units_x': 'mm', 'units_y': 'mm', 'units_z': 'mm', 'units_t': 'ms', 'units': 'mV', 'max_chunk_mb': 0.001})
+    for f in fr:
+        w.imshow(f)
+    w.wait()
+    assert open('sub/b.igb', 'rb').read() == G['igb_b_bytes'].tobytes()          # no-extension name gets .igb, directory is created
+    assert w.nb_chunks() == int(G['igb_b_nchunks']) and w.counter() == fr.shape[0]
+
+
+def test_result_writer_dense_and_sparse_match_the_reference(in_tmp):
+    from pdensorflow_b200.gpuSolve.IO.writers import ResultWriter
+    fr = G['rw_frames']
+    W, H, D = fr.shape[1:]
+    rw = ResultWriter({'width': W, 'height': H, 'depth': D, 'prefix_name': 'cube3D', 'every_N': 2})
+    for f in fr:
+        rw.imshow(f)
+    rw.wait()
+    name = str(G['rw_dense_name'])
+    got = np.load(name)
+    assert got.dtype == G['rw_dense'].dtype and np.array_equal(got, G['rw_dense'])
+    assert rw.nb_chunks() == int(G['rw_dense_nchunks'])
+    rw = ResultWriter({'width': W, 'height': H, 'depth': D, 'prefix_name': 'sp'})
+    rw.set_sparse_domain(G['rw_domain'])
+    for f in fr:
+        rw.imshow(f)
+    rw.wait()
+    d = np.load(str(G['rw_sparse_name']), allow_pickle=True).item()
+    assert tuple(d['dimensions']) == tuple(G['rw_sparse_dimensions'])
+    assert np.array_equal(np.stack(d['indices']), G['rw_sparse_indices'])
+    assert np.array_equal(d['values'], G['rw_sparse_values'])
+    assert not [f for f in os.listdir('.') if '__chunk_' in f]                    # nothing temporary left behind
+    # legacy pre-allocated cube (resultwriter.py:41-47,66-72)
+    rw = ResultWriter({'width': W, 'height': H, 'depth': D, 'prefix_name': 'legacy', 'samples': 4, 'dt_per_plot': 1})
+    rw.initialise_cube()
+    for f in fr:
+        rw.imshow(f)
+    rw.wait()
+    assert np.array_equal(np.load('legacy_{}_{}_{}.npy'.format(H, W, D)), fr)
+
+
+def test_base_writer_chunk_triggers_and_npy_aggregation(in_tmp):
+    from pdensorflow_b200.gpuSolve.IO.writers import BaseWriter
+    fr = G['rw_frames']
+    bw = BaseWriter({'fname': 'out/base', 'max_chunk_mb': 0.001})        # 480-byte frames, 1048-byte chunks: 3 + 2
+    for f in fr:
+        bw.add_solution(f)
+    assert bw.nb_chunks() == 1 and bw.counter() == 5
+    bw.finalize()
+    assert bw.nb_chunks() == 2 and np.array_equal(np.load('out/base.npy'), fr)
+    assert os.listdir('out') == ['base.npy']
+    empty = BaseWriter({'fname': 'none'})
+    empty.finalize()
+    assert np.load('none.npy').shape == (0,)
+    with pytest.raises(ValueError):
+        bw2 = BaseWriter({'fname': 'x'})
+        bw2.add_solution(fr[0])
+        bw2.add_solution(fr[0][:2])
+
+
+def _reference_data(nx, nt):
+    node = np.arange(nx, dtype=np.float32)
+    frame = np.arange(nt, dtype=np.float32)
+    return (np.sin(node)[np.newaxis, :] + 100.0 * frame[:, np.newaxis]).astype(np.float32)
+
+
+@pytest.mark.parametrize('nx,nt', [(300, 5), (63001, 3)], ids=['small', 'large_nx'])
+def test_igb_write_read_roundtrip(tmp_path, nx, nt):
+    """Tests/CICD/unit/test_igb_roundtrip.py:58-84."""
+    from pdensorflow_b200.gpuSolve.IO.readers import IGBReader
+    from pdensorflow_b200.gpuSolve.IO.writers import IGBWriter
+    fname = str(tmp_path / 'roundtrip.igb')
+    ref = _reference_data(nx, nt)
+    writer = IGBWriter({'fname': fname, 'Tend': float(nt - 1), 'nt': nt, 'nx': nx})
+    for t in range(nt):
+        writer.imshow(ref[t, :])
+    writer.wait()
+    reader = IGBReader()
+    reader.read(fname)
+    assert reader.nx() == nx and reader.nt() == nt and reader.ndiff() == 0
+    assert reader.data().shape == (nt, nx)
+    np.testing.assert_allclose(reader.data(), ref, rtol=1.0e-6, atol=1.0e-6)
+    assert reader.dim_t() == float(nt - 1) and reader.org_t() == 0.0
+    assert np.allclose(reader.timevalues(), np.arange(nt))
+    # copy through initialise_from_IGBReader + write_data_to_file (igbwriter.py:190-213)
+    copy = IGBWriter({'fname': str(tmp_path / 'copy.igb')})
+    copy.initialise_from_IGBReader(reader)
+    copy.write_data_to_file()
+    assert open(str(tmp_path / 'copy.igb'), 'rb').read() == open(fname, 'rb').read()
+
+
+def test_reader_tolerates_truncated_and_padded_files(tmp_path):
+    from pdensorflow_b200.gpuSolve.IO.readers import IGBReader
+    from pdensorflow_b200.gpuSolve.IO.writers.igbwriter import igb_header_bytes
+    nx, nt = 10, 4
+    data = _reference_data(nx, nt)
+    short, extra = str(tmp_path / 'short.igb'), str(tmp_path / 'extra.igb')
+    with open(short, 'wb') as f:
+        f.write(igb_header_bytes(nx, 1, 1, nt, 0.0, nt - 1))
+        data.reshape(-1)[:nx * 2 + 3].tofile(f)
+    with open(extra, 'wb') as f:
+        f.write(igb_header_bytes(nx, 1, 1, nt, 0.0, nt - 1))
+        np.concatenate([data.reshape(-1), np.ones(7, np.float32)]).tofile(f)
+    r = IGBReader()
+    r.read(short)
+    assert r.nt() == 2 and np.array_equal(r.data(), data[:2]) and r.ndiff() == nx * 2 + 3 - nx * nt
+    r.read(extra)
+    assert r.nt() == nt and np.array_equal(r.data(), data) and r.ndiff() == 7

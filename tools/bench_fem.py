@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=272)
+    ap.add_argument('--n', '--size', dest='n', type=int, default=272)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--skip-config1', action='store_true')
     ap.add_argument('--layout', default='sell', choices=['sell', 'csr'])

@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=160)
+    ap.add_argument('--n', '--size', dest='n', type=int, default=160)
     ap.add_argument('--steps', type=int, default=20)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
