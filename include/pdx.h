@@ -127,7 +127,10 @@ typedef struct pdx_fd_plan pdx_fd_plan;
  *              1/(2VcF) Cm Vsr/Vc Bufc*Kbufc Kbufc k4 k2 k1 k3 Vrel Bufsr*Kbufsr Kbufsr Vc/Vss Vsr/Vss
  *              1/(2VssF) Bufss*Kbufss Kbufss                                            (45)
  *      states: GCaL GKr GKs Gto CaSR CaSS Cai F F2 FCaSS H J Ki M Nai R R_bar S Xr1 Xr2 Xs D   (22)
- * Arithmetic is always op-for-op fp32 in the reference's order (math_mode is ignored). */
+ * Arithmetic is op-for-op fp32 in the reference's order in both modes; math_mode (pdx_lut_model.math_mode
+ * for the pointwise step, pdx_fd_desc.math_mode for the fused step) only selects how the 4-5 exp / log /
+ * expm1 per node are evaluated: PDX_MATH_EXACT = correctly rounded (fp64 evaluation, bit-comparable with
+ * the oracle, compute bound), PDX_MATH_FAST = fp32 expf / logf / expm1f (<= 2 ulp, HBM bound). */
 typedef struct pdx_lut_table {
     const float* data;       /* device, nrows x stride */
     int32_t nrows, ncols, stride;
@@ -141,6 +144,7 @@ typedef struct pdx_lut_model {
     float   dt;                  /* f32(dt) of the forward-Euler concentration updates */
     pdx_lut_table tab[3];
     float   consts[PDX_LUT_MAX_CONSTS];
+    int32_t math_mode;           /* PDX_MATH_EXACT (0, default) / PDX_MATH_FAST: pointwise step only */
 } pdx_lut_model;
 
 /* IonicModel.differentiate for CRN / TTP (courtemanche_ramirez_nattel.py:423-514,

@@ -44,7 +44,7 @@ class LutTable(C.Structure):
 class LutModel(C.Structure):
     """struct pdx_lut_model (include/pdx.h)."""
     _fields_ = [('model', C.c_int32), ('nconsts', C.c_int32), ('dt', C.c_float), ('tab', LutTable * 3),
-                ('consts', C.c_float * LUT_MAX_CONSTS)]
+                ('consts', C.c_float * LUT_MAX_CONSTS), ('math_mode', C.c_int32)]
 
 
 class PcgPartDesc(C.Structure):

@@ -518,7 +518,8 @@ int pdx_ionic_lut_step(const pdx_lut_model* m, int64_t n, const float* U, float*
         if (!states[i]) { set_error("pdx_ionic_lut_step: null state array"); return 1; }
         L.st[i] = states[i];
     }
-    return launch_lut_ionic(m->model, L, n, U, dU_out, I0, rhs0_out, (cudaStream_t)stream);
+    return launch_lut_ionic(m->model, m->math_mode == PDX_MATH_FAST ? PDX_MATH_FAST : PDX_MATH_EXACT, L, n, U, dU_out, I0,
+                            rhs0_out, (cudaStream_t)stream);
 }
 
 int pdx_fd_enforce_boundary(int ndim, int nx, int ny, int nz, int dirichlet, float value, const float* X, float* out,

@@ -69,8 +69,8 @@ int launch_ionic(int model, int math, const float* params, const float* const* p
 int launch_stim(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s);
 int launch_fd_laplace_aniso(const FdArgs& a, cudaStream_t s);
 int lut_model_num_consts(int model);
-int launch_lut_ionic(int model, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0, float* rhs0,
-                     cudaStream_t s);
+int launch_lut_ionic(int model, int math, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
+                     float* rhs0, cudaStream_t s);
 int launch_fd_lut(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s);
 // TMA-staged tile kernel: requires nz % 4 == 0, 16-byte aligned arrays, HOMOG/HETEROG
 bool fd_tma_supported(const pdx_fd_desc& d);

@@ -9,18 +9,27 @@
 // two rows - and are read through the read-only path, Rush-Larsen (A,B) pairs as 8-byte loads.
 //
 // THIS FILE IS COMPILED WITH -fmad=false: every expression below is evaluated op-for-op in
-// fp32 in the order the reference writes it (IEEE division, no contraction), and
-// exp/log/expm1 return the correctly rounded fp32 value (fp64 evaluation, one rounding) - the
-// oracle's convention - so results are bit-comparable with oracle/ionic_lut.py.  These models
-// move 160-180 B per node-step, so the arithmetic policy costs nothing measurable.
+// fp32 in the order the reference writes it (IEEE division, no contraction).  Two policies for the
+// 4-5 exp/log/expm1 calls per node (PDX_MATH_*):
+//   EXACT  correctly rounded fp32 values (fp64 evaluation, one rounding) - the oracle's convention,
+//          results bit-comparable with oracle/ionic_lut.py.  The fp64 transcendentals cost ~1000
+//          instruction slots per node and make the kernel COMPUTE bound (~52 % of the HBM roofline).
+//   FAST   CUDA's fp32 expf/logf/expm1f (<= 2 ulp); everything else unchanged.  rel-L2 <= 1e-5 against
+//          the oracle (tests/test_ref_golden_gpu.py); the kernel becomes HBM bound.
 #include "pdx_stencil.cuh"
 
 namespace pdx {
 namespace {
 
-__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
-__device__ __forceinline__ float log_cr(float x) { return (float)log((double)x); }
-__device__ __forceinline__ float expm1_cr(float x) { return (float)expm1((double)x); }
+template <int MATH> __device__ __forceinline__ float exp_m(float x) {
+    return MATH == PDX_MATH_EXACT ? (float)exp((double)x) : expf(x);
+}
+template <int MATH> __device__ __forceinline__ float log_m(float x) {
+    return MATH == PDX_MATH_EXACT ? (float)log((double)x) : logf(x);
+}
+template <int MATH> __device__ __forceinline__ float expm1_m(float x) {
+    return MATH == PDX_MATH_EXACT ? (float)expm1((double)x) : expm1f(x);
+}
 
 // Linear interpolation in a uniform table (courtemanche_ramirez_nattel.py:241-252):
 // idx = int((clip(X) - mn)*step), clamped to [0, mx_idx-1]; w = (X - lower)/res.
@@ -62,6 +71,7 @@ enum { CF_u_A = 0, CF_v = 1 };   // v_A, v_B in columns 1,2 (odd start: read as 
 enum { S_Ca_rel = 0, S_Ca_up, S_Cai, S_Ki, S_d, S_f, S_f_Ca, S_h, S_j, S_m, S_oa, S_oi, S_u, S_ua, S_ui, S_v, S_w,
        S_xr, S_xs, CRN_NS };
 
+template <int MATH>
 __device__ __forceinline__ float crn_update(const LutArgs& L, size_t n, float V) {
     const float* c = L.c;
     const float dt = L.dt;
@@ -71,14 +81,14 @@ __device__ __forceinline__ float crn_update(const LutArgs& L, size_t n, float V)
     const Row vr = lookup(L.tab[0], V);
     const Row cr = lookup(L.tab[1], y[S_Cai]);
 
-    const float E_K = c[C_RTF] * log_cr(c[C_KO] / y[S_Ki]);
+    const float E_K = c[C_RTF] * log_m<MATH>(c[C_KO] / y[S_Ki]);
     const float VmEK = V - E_K;
     const float ICaL = vr(CV_ICaL) * y[S_d] * y[S_f] * y[S_f_Ca];
-    const float IKACh = (c[C_KACH] * (0.0517f + 0.4516f / (1.0f + exp_cr((V + 59.53f) / 17.18f)))) * VmEK;
+    const float IKACh = (c[C_KACH] * (0.0517f + 0.4516f / (1.0f + exp_m<MATH>((V + 59.53f) / 17.18f)))) * VmEK;
     const float INa = vr(CV_INa) * y[S_m] * y[S_m] * y[S_m] * y[S_h] * y[S_j];
     const float INaCa = vr(CV_NaCa_a) - y[S_Cai] * vr(CV_NaCa_b);
-    const float IK1 = (c[C_GK1] * VmEK) / (1.0f + exp_cr(0.07f * (V + 80.0f)));
-    const float IKr = ((c[C_GKR] * VmEK) / (1.0f + exp_cr((V + 15.0f) / 22.4f))) * y[S_xr];
+    const float IK1 = (c[C_GK1] * VmEK) / (1.0f + exp_m<MATH>(0.07f * (V + 80.0f)));
+    const float IKr = ((c[C_GKR] * VmEK) / (1.0f + exp_m<MATH>((V + 15.0f) / 22.4f))) * y[S_xr];
     const float IKs = (c[C_GKS] * VmEK) * y[S_xs] * y[S_xs];
     const float IKur = ((c[C_FGKUR] * vr(CV_GKur)) * VmEK) * y[S_ua] * y[S_ua] * y[S_ua] * y[S_ui];
     const float IpCa = cr(CC_IpCa) + vr(CV_IbCa);
@@ -129,6 +139,7 @@ enum { TV_D = 0, TV_F2 = 2, TV_F = 4, TV_H = 6, TV_J = 8, TV_M = 10, TV_R = 12, 
 enum { Q_GCaL = 0, Q_GKr, Q_GKs, Q_Gto, Q_CaSR, Q_CaSS, Q_Cai, Q_F, Q_F2, Q_FCaSS, Q_H, Q_J, Q_Ki, Q_M, Q_Nai, Q_R,
        Q_R_bar, Q_S, Q_Xr1, Q_Xr2, Q_Xs, Q_D, TTP_NS };
 
+template <int MATH>
 __device__ __forceinline__ float ttp_update(const LutArgs& L, size_t n, float V) {
     const float* c = L.c;
     const float dt = L.dt;
@@ -139,14 +150,14 @@ __device__ __forceinline__ float ttp_update(const LutArgs& L, size_t n, float V)
     const Row vr = lookup(L.tab[0], V);
     const Row cr = lookup(L.tab[1], CaSS);
 
-    const float Eca = c[T_HRTONF] * log_cr(c[T_CAO] / Cai);
-    const float Ek = c[T_RTONF] * log_cr(c[T_KO] / Ki);
-    const float Eks = c[T_RTONF] * log_cr(c[T_KOPK] / (Ki + c[T_PKNA] * Nai));
-    const float Ena = c[T_RTONF] * log_cr(c[T_NAO] / Nai);
+    const float Eca = c[T_HRTONF] * log_m<MATH>(c[T_CAO] / Cai);
+    const float Ek = c[T_RTONF] * log_m<MATH>(c[T_KO] / Ki);
+    const float Eks = c[T_RTONF] * log_m<MATH>(c[T_KOPK] / (Ki + c[T_PKNA] * Nai));
+    const float Ena = c[T_RTONF] * log_m<MATH>(c[T_NAO] / Nai);
     const float IpCa = (c[T_GPCA] * Cai) / (c[T_KPCA] + Cai);
     const float v15 = V - 15.0f;
     const float a1 = (y[Q_GCaL] * c[T_FCONST] * c[T_FRT] * 4.0f) *
-                     (fabsf(v15) < 1e-10f ? c[T_HFRT] : v15 / expm1_cr(2.0f * v15 * c[T_FRT]));
+                     (fabsf(v15) < 1e-10f ? c[T_HFRT] : v15 / expm1_m<MATH>(2.0f * v15 * c[T_FRT]));
     const float ICaL_A = a1 * vr(TV_a2);
     const float ICaL_B = a1 * c[T_CAO];
     const float IKr = y[Q_GKr] * c[T_SQRTKO] * y[Q_Xr1] * y[Q_Xr2] * (V - Ek);
@@ -204,28 +215,28 @@ __device__ __forceinline__ float ttp_update(const LutArgs& L, size_t n, float V)
     return -Iion;
 }
 
-template <int MODEL>
+template <int MODEL, int MATH>
 __device__ __forceinline__ float lut_update(const LutArgs& L, size_t n, float V) {
-    return MODEL == PDX_MODEL_CRN ? crn_update(L, n, V) : ttp_update(L, n, V);
+    return MODEL == PDX_MODEL_CRN ? crn_update<MATH>(L, n, V) : ttp_update<MATH>(L, n, V);
 }
 
 // ---------------------------------------------------------------------------- kernels
 // IonicModel.differentiate (+ RHS0 = U + dt*(dU + I0) of MonodomainSolver.solve_step)
-template <int MODEL>
-__global__ void __launch_bounds__(128) lut_ionic_kernel(const __grid_constant__ LutArgs L, int64_t n, const float* U,
+template <int MODEL, int MATH>
+__global__ void __launch_bounds__(128, 5) lut_ionic_kernel(const __grid_constant__ LutArgs L, int64_t n, const float* U,
                                                         float* dU, const float* I0, float* rhs0) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float V = U[i];
-        const float d = lut_update<MODEL>(L, (size_t)i, V);
+        const float d = lut_update<MODEL, MATH>(L, (size_t)i, V);
         if (dU) dU[i] = d;
         if (rhs0) rhs0[i] = V + L.dt * (d + (I0 ? I0[i] : 0.0f));
     }
 }
 
 // fused explicit FD step: U1 = (U0 + dt*dU(U)) + coef*lap(U0)  (Tests/FD/Fenton/fenton.py:90-99)
-template <int MODEL, int LAP>
-__global__ void __launch_bounds__(128) lut_fd_kernel(const __grid_constant__ FdArgs a,
+template <int MODEL, int LAP, int MATH>
+__global__ void __launch_bounds__(128, 5) lut_fd_kernel(const __grid_constant__ FdArgs a,
                                                      const __grid_constant__ LutArgs L) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -235,24 +246,24 @@ __global__ void __launch_bounds__(128) lut_fd_kernel(const __grid_constant__ FdA
     const Field f = make_field(a);
     float c;
     const float lap = node_laplacian<LAP, PDX_MATH_EXACT>(a, f, i, j, k, c);
-    const float dU = lut_update<MODEL>(L, idx, a.Uin[idx]);      // raw U, not U0
+    const float dU = lut_update<MODEL, MATH>(L, idx, a.Uin[idx]);      // raw U, not U0
     const float u_new = (c + a.dt * dU) + a.coef * lap;
     a.Uout[idx] = u_new;
     if (a.mirror_lo && i == a.mirror_lo_plane) a.mirror_lo[(size_t)j * a.nz + k] = u_new;
     if (a.mirror_hi && i == a.mirror_hi_plane) a.mirror_hi[(size_t)j * a.nz + k] = u_new;
 }
 
-template <int MODEL>
+template <int MODEL, int MATH>
 int launch_fd_lap(int lap, const FdArgs& a, const LutArgs& L, cudaStream_t s) {
     if (a.xe <= a.xb) return 0;
     dim3 block(32, 4, 1);
     dim3 grid((a.nz + 31) / 32, (a.ny + 3) / 4, a.xe - a.xb);
     if (grid.z > 65535u || grid.y > 65535u) { set_error("LUT-model FD kernel: grid too large"); return 1; }
     switch (lap) {
-        case PDX_LAP_HOMOG:   lut_fd_kernel<MODEL, PDX_LAP_HOMOG><<<grid, block, 0, s>>>(a, L); break;
-        case PDX_LAP_CONV:    lut_fd_kernel<MODEL, PDX_LAP_CONV><<<grid, block, 0, s>>>(a, L); break;
-        case PDX_LAP_HETEROG: lut_fd_kernel<MODEL, PDX_LAP_HETEROG><<<grid, block, 0, s>>>(a, L); break;
-        case PDX_LAP_ANISO:   lut_fd_kernel<MODEL, PDX_LAP_ANISO><<<grid, block, 0, s>>>(a, L); break;
+        case PDX_LAP_HOMOG:   lut_fd_kernel<MODEL, PDX_LAP_HOMOG, MATH><<<grid, block, 0, s>>>(a, L); break;
+        case PDX_LAP_CONV:    lut_fd_kernel<MODEL, PDX_LAP_CONV, MATH><<<grid, block, 0, s>>>(a, L); break;
+        case PDX_LAP_HETEROG: lut_fd_kernel<MODEL, PDX_LAP_HETEROG, MATH><<<grid, block, 0, s>>>(a, L); break;
+        case PDX_LAP_ANISO:   lut_fd_kernel<MODEL, PDX_LAP_ANISO, MATH><<<grid, block, 0, s>>>(a, L); break;
         default: set_error("unknown lap_kind"); return 1;
     }
     count_launch();
@@ -265,21 +276,31 @@ int lut_model_num_consts(int model) {
     return model == PDX_MODEL_CRN ? (int)C_NCONST : model == PDX_MODEL_TTP ? (int)T_NCONST : -1;
 }
 
-int launch_lut_ionic(int model, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0, float* rhs0,
-                     cudaStream_t s) {
+int launch_lut_ionic(int model, int math, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
+                     float* rhs0, cudaStream_t s) {
     int64_t nb = (n + 127) / 128;
     if (nb > 148 * 32) nb = 148 * 32;
     if (nb < 1) nb = 1;
-    if (model == PDX_MODEL_CRN) lut_ionic_kernel<PDX_MODEL_CRN><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
-    else if (model == PDX_MODEL_TTP) lut_ionic_kernel<PDX_MODEL_TTP><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
-    else { set_error("not a lookup-table model"); return 1; }
+    const bool ex = math == PDX_MATH_EXACT;
+    if (model == PDX_MODEL_CRN) {
+        if (ex) lut_ionic_kernel<PDX_MODEL_CRN, PDX_MATH_EXACT><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
+        else lut_ionic_kernel<PDX_MODEL_CRN, PDX_MATH_FAST><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
+    } else if (model == PDX_MODEL_TTP) {
+        if (ex) lut_ionic_kernel<PDX_MODEL_TTP, PDX_MATH_EXACT><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
+        else lut_ionic_kernel<PDX_MODEL_TTP, PDX_MATH_FAST><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
+    } else { set_error("not a lookup-table model"); return 1; }
     count_launch();
     return check_cuda(cudaGetLastError(), "lut_ionic_kernel launch");
 }
 
 int launch_fd_lut(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s) {
-    if (d.model == PDX_MODEL_CRN) return launch_fd_lap<PDX_MODEL_CRN>(d.lap_kind, a, L, s);
-    if (d.model == PDX_MODEL_TTP) return launch_fd_lap<PDX_MODEL_TTP>(d.lap_kind, a, L, s);
+    const bool ex = d.math_mode == PDX_MATH_EXACT;
+    if (d.model == PDX_MODEL_CRN)
+        return ex ? launch_fd_lap<PDX_MODEL_CRN, PDX_MATH_EXACT>(d.lap_kind, a, L, s)
+                  : launch_fd_lap<PDX_MODEL_CRN, PDX_MATH_FAST>(d.lap_kind, a, L, s);
+    if (d.model == PDX_MODEL_TTP)
+        return ex ? launch_fd_lap<PDX_MODEL_TTP, PDX_MATH_EXACT>(d.lap_kind, a, L, s)
+                  : launch_fd_lap<PDX_MODEL_TTP, PDX_MATH_FAST>(d.lap_kind, a, L, s);
     set_error("not a lookup-table model");
     return 1;
 }

@@ -99,7 +99,7 @@ class LutIonicModel(IonicModel):
         """struct pdx_lut_model for the current tables, constants and dt."""
         if self._tables is None:
             raise L.PdxError('initialize_state_variables(U) must be called first (it builds the lookup tables)')
-        if self._desc is None or self._desc_dt != self._dt:
+        if self._desc is None or self._desc_dt != self._dt or self._desc_math != self.math_mode:
             d = L.LutModel()
             d.model = self._MODEL_ID
             consts = self._fold_constants()
@@ -109,7 +109,8 @@ class LutIonicModel(IonicModel):
                 d.consts[i] = float(np.float32(v))
             for i, t in enumerate(self._tables):
                 t.fill_desc(d.tab[i])
-            self._desc, self._desc_dt = d, self._dt
+            d.math_mode = L.MATH_FAST if self.math_mode == 'fast' else L.MATH_EXACT
+            self._desc, self._desc_dt, self._desc_math = d, self._dt, self.math_mode
         return self._desc
 
     def set_parameter(self, pname, pvalue):

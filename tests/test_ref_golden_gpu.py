@@ -204,10 +204,11 @@ def test_fd_heterogeneous_steps_vs_reference_source(cuda):
 
 # ------------------------------------------------------------------------------ fused FD + LUT models
 @pytest.mark.parametrize('tag', ['crn', 'ttp'])
-@pytest.mark.parametrize('lap', ['homog', 'heterog'])
-def test_fused_fd_step_with_lut_models_vs_oracle(cuda, tag, lap):
+@pytest.mark.parametrize('lap,math', [('homog', 'exact'), ('heterog', 'exact'), ('homog', 'fast')])
+def test_fused_fd_step_with_lut_models_vs_oracle(cuda, tag, lap, math):
     """The reference has no FD script for CRN/TTP; the oracle's fd_run with the (reference-pinned)
-    oracle models is the arbiter.  S1 plane wave, 60 steps at dt = 0.02."""
+    oracle models is the arbiter.  S1 plane wave, 60 steps at dt = 0.02.  EXACT (correctly rounded
+    exp/log, bit-comparable) <= 1e-6; FAST (fp32 expf/logf, the HBM-bound variant) <= 1e-5."""
     from pdensorflow_b200.fd import FDStepper
     shape, spacing, dt, diff, nsteps = (12, 10, 16), (0.25, 0.25, 0.25), 0.02, 0.1, 60
     mo = ol.CourtemancheRamirezNattel() if tag == 'crn' else ol.TenTusscherPanfilov()
@@ -221,15 +222,16 @@ def test_fused_fd_step_with_lut_models_vs_oracle(cuda, tag, lap):
     mo.initialize_state_variables(U)
     Uo = ofd.fd_run(mo, U.copy(), nsteps, dt, diff, spacing, DIFF=Dm)
     mg = _lut(tag)
-    st = FDStepper(shape, spacing, dt, diff, model=mg, lap=lap, DIFF=Dm)
+    st = FDStepper(shape, spacing, dt, diff, model=mg, lap=lap, DIFF=Dm, math=math)
     assert st.kernel == 'generic'
     st.set_U(U)
     st.step(nsteps)
     assert np.isfinite(host(st.U())).all()
-    assert rel_l2(host(st.U()), Uo) <= 1e-6, rel_l2(host(st.U()), Uo)
+    tol = 1e-6 if math == 'exact' else 1e-5
+    assert rel_l2(host(st.U()), Uo) <= tol, rel_l2(host(st.U()), Uo)
     key = 'Cai'
     attr = '_Cai'
-    assert rel_l2(host(getattr(mg, attr)), mo.s[key]) <= 1e-5
+    assert rel_l2(host(getattr(mg, attr)), mo.s[key]) <= 10 * tol
 
 
 def test_fused_anisotropic_step_vs_oracle(cuda):

@@ -54,6 +54,11 @@ def bench(shape, model='fenton4v', math='fast', kernel='auto', lap='homog', nste
 if __name__ == '__main__':
     torch.cuda.set_device(0)
     S = (512, 512, 512)
+    if '--lut' in sys.argv:            # only the lookup-table models, both arithmetic policies
+        for m in ('crn', 'ttp'):
+            for mm in ('fast', 'exact'):
+                bench((256, 256, 256), model=m, nsteps=10, math=mm)
+        sys.exit(0)
     bench(S)
     bench(S, math='exact')
     bench(S, kernel='generic')
@@ -65,3 +70,5 @@ if __name__ == '__main__':
     bench((4096, 4096), nsteps=100)
     bench((256, 256, 256), model='crn', nsteps=10)
     bench((256, 256, 256), model='ttp', nsteps=10)
+    bench((256, 256, 256), model='crn', nsteps=10, math='exact')
+    bench((256, 256, 256), model='ttp', nsteps=10, math='exact')
