@@ -16,9 +16,14 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 BUILD = os.path.join(HERE, 'build')
 LIB = os.path.join(PKG, 'libpdx.so')
-SOURCES = ['pdx_api.cu', 'pdx_fd_generic.cu', 'pdx_fd_tma.cu', 'pdx_fd_resident.cu', 'pdx_fem.cu', 'pdx_fem_part.cu', 'pdx_ionic_lut.cu']
-# per-source flags: the lookup-table models are evaluated op-for-op (no FMA contraction)
-EXTRA = {'pdx_ionic_lut.cu': ['-fmad=false']}
+# (source, object, extra flags).  pdx_ionic_lut.cu is compiled TWICE: the EXACT kernels op-for-op (no FMA
+# contraction, IEEE division), the FAST kernels with contraction and approximate division (see its header).
+UNITS = [('pdx_api.cu', 'pdx_api.o', []), ('pdx_fd_generic.cu', 'pdx_fd_generic.o', []),
+         ('pdx_fd_tma.cu', 'pdx_fd_tma.o', []), ('pdx_fd_resident.cu', 'pdx_fd_resident.o', []),
+         ('pdx_fem.cu', 'pdx_fem.o', []), ('pdx_fem_part.cu', 'pdx_fem_part.o', []),
+         ('pdx_ionic_lut.cu', 'pdx_ionic_lut.o', ['-fmad=false', '-DPDX_LUT_TU_MATH=0']),
+         ('pdx_ionic_lut.cu', 'pdx_ionic_lut_fast.o', ['-fmad=true', '-prec-div=false', '-DPDX_LUT_TU_MATH=1'])]
+SOURCES = sorted({u[0] for u in UNITS})
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr']
@@ -48,12 +53,12 @@ def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     jobs = []
-    for s in SOURCES:
+    for s, o, extra in UNITS:
         src = os.path.join(HERE, s)
-        obj = os.path.join(BUILD, s.replace('.cu', '.o'))
+        obj = os.path.join(BUILD, o)
         if force or _stale(src, obj):
-            cmd = [nvcc] + ARCH + FLAGS + EXTRA.get(s, []) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
-            jobs.append((s, cmd))
+            cmd = [nvcc] + ARCH + FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            jobs.append((o, cmd))
 
     def run(job):
         name, cmd = job
@@ -67,7 +72,7 @@ def build(force=False, verbose=False):
                     sys.stderr.write('--- %s\n%s%s\n' % (name, r.stdout, r.stderr))
                 if r.returncode != 0:
                     raise RuntimeError('nvcc failed on %s' % name)
-    objs = [os.path.join(BUILD, s.replace('.cu', '.o')) for s in SOURCES]
+    objs = [os.path.join(BUILD, o) for _, o, _ in UNITS]
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc] + ARCH + ['-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC']
         r = subprocess.run(cmd, capture_output=True, text=True)

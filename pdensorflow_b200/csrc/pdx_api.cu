@@ -378,7 +378,7 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
     a.xb = xb; a.xe = xe;
     if (xe <= xb) return 0;
     if (lut) {
-        const int rc = launch_fd_lut(d, a, p->lut, s);
+        const int rc = d.math_mode == PDX_MATH_FAST ? launch_fd_lut_fast(d, a, p->lut, s) : launch_fd_lut_exact(d, a, p->lut, s);
         if (!rc) p->launches += 1;
         return rc;
     }
@@ -518,8 +518,8 @@ int pdx_ionic_lut_step(const pdx_lut_model* m, int64_t n, const float* U, float*
         if (!states[i]) { set_error("pdx_ionic_lut_step: null state array"); return 1; }
         L.st[i] = states[i];
     }
-    return launch_lut_ionic(m->model, m->math_mode == PDX_MATH_FAST ? PDX_MATH_FAST : PDX_MATH_EXACT, L, n, U, dU_out, I0,
-                            rhs0_out, (cudaStream_t)stream);
+    return m->math_mode == PDX_MATH_FAST ? launch_lut_ionic_fast(m->model, L, n, U, dU_out, I0, rhs0_out, (cudaStream_t)stream)
+                                         : launch_lut_ionic_exact(m->model, L, n, U, dU_out, I0, rhs0_out, (cudaStream_t)stream);
 }
 
 int pdx_fd_enforce_boundary(int ndim, int nx, int ny, int nz, int dirichlet, float value, const float* X, float* out,

@@ -94,9 +94,10 @@ struct PartArgs {
 
 // All-reduce of NV (1 or 2) scalars over the ranks.  Returns false when a peer timed out.
 // Every thread of the grid calls it; loc[] are the thread's partial sums.
+// `pushed`: this thread has stored into a neighbour's window since the last all-reduce.
 template <int NV>
 __device__ __forceinline__ bool all_reduce(const PartArgs& a, cg::grid_group& grid, unsigned int& epoch, float* sh,
-                                           float loc0, float loc1, float* out0, float* out1) {
+                                           float loc0, float loc1, float* out0, float* out1, bool pushed) {
     const int nb = gridDim.x;
     float v0 = block_sum(loc0, sh);
     float v1 = NV > 1 ? block_sum(loc1, sh) : 0.0f;
@@ -104,7 +105,7 @@ __device__ __forceinline__ bool all_reduce(const PartArgs& a, cg::grid_group& gr
         __stcg(a.part + blockIdx.x, v0);
         if (NV > 1) __stcg(a.part + nb + blockIdx.x, v1);
     }
-    __threadfence_system();          // this thread's peer stores (z of the edge rows) before the publication
+    if (pushed) __threadfence_system();   // this thread's peer stores (z of the edge rows) before the publication
     grid.sync();
     ++epoch;
     const int par = epoch & 1;
@@ -201,7 +202,7 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, const float* xa, con
 }
 
 template <int G>
-__global__ void __launch_bounds__(256) pcg_part_kernel(const __grid_constant__ PartArgs a) {
+__global__ void __launch_bounds__(256, 8) pcg_part_kernel(const __grid_constant__ PartArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[33];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,19 +213,20 @@ __global__ void __launch_bounds__(256) pcg_part_kernel(const __grid_constant__ P
 
     // b = M rhs0 (optional) ; r = b - A x ; z = Minv r ; p = z ; rz = r.z      (conjgrad.py:191-203)
     float loc_rz = 0.0f, loc_rr = 0.0f;
+    bool pushed = false;
     rows_dot<G>(a, a.x, a.mval, a.rhs0, [&](int row, float ax, float bm) {
         const float bv = a.mval ? bm : a.b[row];
         const float r = __fsub_rn(bv, ax);
         const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
         __stcg(a.r + row, r);
         __stcg(a.p + glo + row, z);
-        if (row < a.send_lo) a.peer_lo_p[row] = z;                 // the neighbours' ghost p = z
-        if (row >= hi_first) a.peer_hi_p[row - hi_first] = z;
+        if (row < a.send_lo) { a.peer_lo_p[row] = z; pushed = true; }          // the neighbours' ghost p = z
+        if (row >= hi_first) { a.peer_hi_p[row - hi_first] = z; pushed = true; }
         loc_rz = fmaf(r, z, loc_rz);
         loc_rr = fmaf(r, r, loc_rr);
     });
     float rz, res;
-    bool ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rz, &res);
+    bool ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rz, &res, pushed);
 
     int niters = 0, flags = 0;
     for (int k = 1; ok && k <= a.maxiter; ++k) {
@@ -236,19 +238,20 @@ __global__ void __launch_bounds__(256) pcg_part_kernel(const __grid_constant__ P
             loc_pq = fmaf(__ldcg(a.p + glo + row), ap, loc_pq);
         });
         float pq, unused;
-        ok = all_reduce<1>(a, grid, epoch, sh, loc_pq, 0.0f, &pq, &unused);
+        ok = all_reduce<1>(a, grid, epoch, sh, loc_pq, 0.0f, &pq, &unused, false);
         if (!ok) break;
         const float alpha = rz / pq;
         // x += alpha p ; r -= alpha q ; res = r.r ; z = Minv r ; rz' = r.z        (conjgrad.py:172-183)
         loc_rz = 0.0f; loc_rr = 0.0f;
+        pushed = false;
         for (int i = tid; i < a.n; i += nthreads) {
             const float pi = __ldcg(a.p + glo + i);
             __stcg(a.x + glo + i, fmaf(alpha, pi, __ldcg(a.x + glo + i)));
             const float r = fmaf(-alpha, __ldcg(a.q + i), __ldcg(a.r + i));
             __stcg(a.r + i, r);
             const float z = a.minv ? __fmul_rn(a.minv[i], r) : r;
-            if (i < a.send_lo) a.peer_lo_zg[i] = z;                    // edge rows: z into the neighbours' ghost slots
-            if (i >= hi_first) a.peer_hi_zg[i - hi_first] = z;
+            if (i < a.send_lo) { a.peer_lo_zg[i] = z; pushed = true; }            // edge rows: z into the neighbours' ghost slots
+            if (i >= hi_first) { a.peer_hi_zg[i - hi_first] = z; pushed = true; }
             loc_rr = fmaf(r, r, loc_rr);
             loc_rz = fmaf(r, z, loc_rz);
         }
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(256) pcg_part_kernel(const __grid_constant__ P
             __stcg(a.x + w, fmaf(alpha, __ldcg(a.p + w), __ldcg(a.x + w)));
         }
         float rznew;
-        ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rznew, &res);
+        ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rznew, &res, pushed);
         if (!ok) break;
         // batched convergence test + NaN/Inf guard (conjgrad.py:293-300); p is not needed after the last iteration
         if (k % a.check_every == 0) {

@@ -69,9 +69,13 @@ int launch_ionic(int model, int math, const float* params, const float* const* p
 int launch_stim(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s);
 int launch_fd_laplace_aniso(const FdArgs& a, cudaStream_t s);
 int lut_model_num_consts(int model);
-int launch_lut_ionic(int model, int math, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
-                     float* rhs0, cudaStream_t s);
-int launch_fd_lut(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s);
+// one translation unit per arithmetic policy (pdx_ionic_lut.cu is compiled twice)
+int launch_lut_ionic_exact(int model, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
+                           float* rhs0, cudaStream_t s);
+int launch_lut_ionic_fast(int model, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
+                          float* rhs0, cudaStream_t s);
+int launch_fd_lut_exact(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s);
+int launch_fd_lut_fast(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s);
 // TMA-staged tile kernel: requires nz % 4 == 0, 16-byte aligned arrays, HOMOG/HETEROG
 bool fd_tma_supported(const pdx_fd_desc& d);
 // mapS: per-state tensor maps (box = fd_tma_state_box) to stage the states by TMA, or nullptr to

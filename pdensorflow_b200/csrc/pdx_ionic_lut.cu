@@ -8,18 +8,23 @@
 // accesses); the three tables (0.5-12 MB) stay L2/L1 resident - neighbouring nodes hit the same
 // two rows - and are read through the read-only path, Rush-Larsen (A,B) pairs as 8-byte loads.
 //
-// THIS FILE IS COMPILED WITH -fmad=false: every expression below is evaluated op-for-op in
-// fp32 in the order the reference writes it (IEEE division, no contraction).  Two policies for the
-// 4-5 exp/log/expm1 calls per node (PDX_MATH_*):
-//   EXACT  correctly rounded fp32 values (fp64 evaluation, one rounding) - the oracle's convention,
-//          results bit-comparable with oracle/ionic_lut.py.  The fp64 transcendentals cost ~1000
-//          instruction slots per node and make the kernel COMPUTE bound (~52 % of the HBM roofline).
-//   FAST   CUDA's fp32 expf/logf/expm1f (<= 2 ulp); everything else unchanged.  rel-L2 <= 1e-5 against
-//          the oracle (tests/test_ref_golden_gpu.py); the kernel becomes HBM bound.
+// THIS FILE IS COMPILED TWICE (csrc/build.py), once per arithmetic policy (PDX_LUT_TU_MATH = PDX_MATH_*):
+//   EXACT  -fmad=false: every expression is evaluated op-for-op in fp32 in the order the reference writes
+//          it (IEEE division, no contraction) and exp/log/expm1 return the correctly rounded fp32 value
+//          (fp64 evaluation, one rounding) - the oracle's convention, results bit-comparable with
+//          oracle/ionic_lut.py.  ~1400 instructions per node: the kernel is issue/latency bound.
+//   FAST   same formulas, FMA contraction allowed, approximate division (-prec-div=false, 2 ulp) and
+//          CUDA's fp32 expf/logf/expm1f.  rel-L2 <= 1e-5 against the oracle (tests/test_ref_golden_gpu.py).
 #include "pdx_stencil.cuh"
+
+#ifndef PDX_LUT_TU_MATH
+#define PDX_LUT_TU_MATH PDX_MATH_EXACT
+#endif
 
 namespace pdx {
 namespace {
+
+constexpr int TU_MATH = PDX_LUT_TU_MATH;
 
 template <int MATH> __device__ __forceinline__ float exp_m(float x) {
     return MATH == PDX_MATH_EXACT ? (float)exp((double)x) : expf(x);
@@ -223,7 +228,7 @@ __device__ __forceinline__ float lut_update(const LutArgs& L, size_t n, float V)
 // ---------------------------------------------------------------------------- kernels
 // IonicModel.differentiate (+ RHS0 = U + dt*(dU + I0) of MonodomainSolver.solve_step)
 template <int MODEL, int MATH>
-__global__ void __launch_bounds__(128, 5) lut_ionic_kernel(const __grid_constant__ LutArgs L, int64_t n, const float* U,
+__global__ void __launch_bounds__(128, 8) lut_ionic_kernel(const __grid_constant__ LutArgs L, int64_t n, const float* U,
                                                         float* dU, const float* I0, float* rhs0) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(128, 5) lut_ionic_kernel(const __grid_constant
 
 // fused explicit FD step: U1 = (U0 + dt*dU(U)) + coef*lap(U0)  (Tests/FD/Fenton/fenton.py:90-99)
 template <int MODEL, int LAP, int MATH>
-__global__ void __launch_bounds__(128, 5) lut_fd_kernel(const __grid_constant__ FdArgs a,
+__global__ void __launch_bounds__(128, 8) lut_fd_kernel(const __grid_constant__ FdArgs a,
                                                      const __grid_constant__ LutArgs L) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(128, 5) lut_fd_kernel(const __grid_constant__ 
     const size_t idx = ((size_t)i * a.ny + j) * a.nz + k;
     const Field f = make_field(a);
     float c;
-    const float lap = node_laplacian<LAP, PDX_MATH_EXACT>(a, f, i, j, k, c);
+    const float lap = node_laplacian<LAP, LAP == PDX_LAP_ANISO ? PDX_MATH_EXACT : MATH>(a, f, i, j, k, c);
     const float dU = lut_update<MODEL, MATH>(L, idx, a.Uin[idx]);      // raw U, not U0
     const float u_new = (c + a.dt * dU) + a.coef * lap;
     a.Uout[idx] = u_new;
@@ -272,35 +277,30 @@ int launch_fd_lap(int lap, const FdArgs& a, const LutArgs& L, cudaStream_t s) {
 
 }  // namespace
 
+#if PDX_LUT_TU_MATH == 0
 int lut_model_num_consts(int model) {
     return model == PDX_MODEL_CRN ? (int)C_NCONST : model == PDX_MODEL_TTP ? (int)T_NCONST : -1;
 }
+#define PDX_LUT_FN(name) name##_exact
+#else
+#define PDX_LUT_FN(name) name##_fast
+#endif
 
-int launch_lut_ionic(int model, int math, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
-                     float* rhs0, cudaStream_t s) {
+int PDX_LUT_FN(launch_lut_ionic)(int model, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
+                                 float* rhs0, cudaStream_t s) {
     int64_t nb = (n + 127) / 128;
     if (nb > 148 * 32) nb = 148 * 32;
     if (nb < 1) nb = 1;
-    const bool ex = math == PDX_MATH_EXACT;
-    if (model == PDX_MODEL_CRN) {
-        if (ex) lut_ionic_kernel<PDX_MODEL_CRN, PDX_MATH_EXACT><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
-        else lut_ionic_kernel<PDX_MODEL_CRN, PDX_MATH_FAST><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
-    } else if (model == PDX_MODEL_TTP) {
-        if (ex) lut_ionic_kernel<PDX_MODEL_TTP, PDX_MATH_EXACT><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
-        else lut_ionic_kernel<PDX_MODEL_TTP, PDX_MATH_FAST><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
-    } else { set_error("not a lookup-table model"); return 1; }
+    if (model == PDX_MODEL_CRN) lut_ionic_kernel<PDX_MODEL_CRN, TU_MATH><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
+    else if (model == PDX_MODEL_TTP) lut_ionic_kernel<PDX_MODEL_TTP, TU_MATH><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
+    else { set_error("not a lookup-table model"); return 1; }
     count_launch();
     return check_cuda(cudaGetLastError(), "lut_ionic_kernel launch");
 }
 
-int launch_fd_lut(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s) {
-    const bool ex = d.math_mode == PDX_MATH_EXACT;
-    if (d.model == PDX_MODEL_CRN)
-        return ex ? launch_fd_lap<PDX_MODEL_CRN, PDX_MATH_EXACT>(d.lap_kind, a, L, s)
-                  : launch_fd_lap<PDX_MODEL_CRN, PDX_MATH_FAST>(d.lap_kind, a, L, s);
-    if (d.model == PDX_MODEL_TTP)
-        return ex ? launch_fd_lap<PDX_MODEL_TTP, PDX_MATH_EXACT>(d.lap_kind, a, L, s)
-                  : launch_fd_lap<PDX_MODEL_TTP, PDX_MATH_FAST>(d.lap_kind, a, L, s);
+int PDX_LUT_FN(launch_fd_lut)(const pdx_fd_desc& d, const FdArgs& a, const LutArgs& L, cudaStream_t s) {
+    if (d.model == PDX_MODEL_CRN) return launch_fd_lap<PDX_MODEL_CRN, TU_MATH>(d.lap_kind, a, L, s);
+    if (d.model == PDX_MODEL_TTP) return launch_fd_lap<PDX_MODEL_TTP, TU_MATH>(d.lap_kind, a, L, s);
     set_error("not a lookup-table model");
     return 1;
 }
