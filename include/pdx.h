@@ -331,6 +331,22 @@ int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s);
 int     pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, const float* rhs0, float* x, int maxiter,
                            double toll, int check_every, int32_t* info /* device, 4 words */, void* stream);
 
+/* ------------------------------------------------------------------ FEM assembly on the device */
+/* P1 mass / stiffness assembly (gpuSolve/matrices/globalMatrices.py:82-287, localMass.py,
+ * localStiffness.py): one thread per element evaluates the contravariant basis, the measure and the
+ * nv x nv local matrices in fp64 and adds them (fp64 atomics) into CSR-ordered accumulators at the
+ * positions of (row, col) in the given pattern (columns sorted inside each row).
+ *  nv 2 / 3 / 4 = Edges / Trias / Tetras; elems [ne][elem_stride] int32 holds the nv vertex ids first
+ *  (the reference keeps the region id in the last column); pts fp64 [npt][3]; rowid (or NULL) maps a
+ *  vertex id to its matrix row (RCM renumbering: iperm); sigma fp64 [ne][6] = xx xy xz yy yz zz of the
+ *  diffusion tensor (NULL = identity).  mass_acc / stiff_acc: fp64 [nnz], zeroed by the caller, either may
+ *  be NULL.  *status (device int32) is set to 1 if an entry is missing from the pattern.
+ * pdx_round_to_f32 turns the accumulators into the fp32 value arrays the solvers use. */
+int pdx_fem_assemble(int nv, int64_t ne, const int32_t* elems, int elem_stride, const double* pts,
+                     const int32_t* rowid, const double* sigma, const int32_t* rowptr, const int32_t* col,
+                     double* mass_acc, double* stiff_acc, int32_t* status, void* stream);
+int pdx_round_to_f32(const double* in, float* out, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------ misc */
 int         pdx_version(void);
 const char* pdx_last_error(void);

@@ -29,6 +29,7 @@ class HeatSolver:
         self._Tend = 10
         self._use_renumbering = False
         self._explicit_lumped = False     # opt-in (not in the reference): explicit mass-lumped step
+        self._device_assembly = None      # None: on the device above DEVICE_ASSEMBLY_MIN_ELEMENTS elements; True / False
         if cfgdict is not None:
             for attribute in list(self.__dict__.keys()):
                 if attribute[1:] in cfgdict.keys():
@@ -66,13 +67,21 @@ class HeatSolver:
         self._materials.add_ud_function(fname, fsign)
 
     def assemble_matrices(self):
+        from ..matrices import device_assembly as DA
         connectivity = self._Domain.mesh_connectivity('True')
         pattern = compute_coo_pattern(connectivity)
         if self._use_renumbering:
             self._renumbering = compute_reverse_cuthill_mckee_indexing(pattern)
         lmatr = {'mass': localMass, 'stiffness': localStiffness}
-        MATRICES = assemble_matrices_dict(lmatr, pattern, self._Domain, self._materials, connectivity,
-                                          renumbering=self._renumbering)
+        nelem = sum(E.shape[0] for E in self._Domain.Elems().values())
+        on_device = self._device_assembly
+        if on_device is None:
+            on_device = nelem >= DA.DEVICE_ASSEMBLY_MIN_ELEMENTS and DA.supported(self._Domain, self._materials)
+        if on_device:      # one thread per element, fp64 atomics into CSR order (pdx_fem_assemble)
+            MATRICES = DA.assemble_on_device(self._Domain, self._materials, renumbering=self._renumbering)
+        else:
+            MATRICES = assemble_matrices_dict(lmatr, pattern, self._Domain, self._materials, connectivity,
+                                              renumbering=self._renumbering)
         self._MASS = MATRICES['mass']
         self._STIFFNESS = MATRICES['stiffness']
         A = csr_axpby(self._MASS, 1.0, self._STIFFNESS, self._dt)

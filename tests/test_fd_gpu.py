@@ -278,3 +278,36 @@ def test_full_size_plane_wave_property(cuda):
         assert abs(tot - float(col.astype(np.float64).sum()) * n * n) <= 1e-9 * abs(tot) + 1e-3
         del st, U, Ug
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize('kernel', ['tma', 'generic'])
+def test_index_arithmetic_beyond_2_31_nodes(cuda, kernel):
+    """Maximum sizes: a slab of 520 x 2048 x 2048 = 2.18e9 nodes (config 4 keeps 128-512 planes of 2048^2 per GPU)
+    has element offsets beyond 2^31.  The field repeats every 8 planes along x, so - two planes away from the slab's
+    ends - the solution does too: planes 512.. (offsets >= 2^31) must equal planes 16.. BITWISE, and both must equal
+    the same 8-plane pattern advanced on a small 48-plane grid."""
+    from pdensorflow_b200.fd import FDStepper
+    nx, ny, nz, period, nsteps = 520, 2048, 2048, 8, 2
+    free, _ = torch.cuda.mem_get_info()
+    if free < 5.5 * nx * ny * nz * 4:
+        pytest.skip('not enough device memory for 2.18e9 nodes')
+    g = torch.Generator(device='cuda').manual_seed(3)
+    block = torch.rand((period, ny, nz), generator=g, device='cuda') * 100.0 - 80.0
+
+    def run(planes):
+        st = FDStepper((planes, ny, nz), (1.0, 1.0, 1.0), 0.1, 0.8, model='fenton4v', math='exact', kernel=kernel)
+        st.U().view(planes // period, period, ny, nz).copy_(block.unsqueeze(0).expand(planes // period, -1, -1, -1))
+        st.step(nsteps)
+        torch.cuda.synchronize()
+        return st
+
+    big = run(nx)
+    assert big.U().numel() > 2 ** 31
+    hi, lo = big.U()[512:516], big.U()[16:20]
+    assert bool(torch.isfinite(hi).all()) and torch.equal(hi, lo)
+    assert torch.equal(big.states[0][512:516], big.states[0][16:20])
+    keep = lo.clone()
+    del big, hi, lo
+    torch.cuda.empty_cache()
+    small = run(48)
+    assert torch.equal(small.U()[16:20], keep)
