@@ -89,7 +89,7 @@ class PartitionedExplicitFEM:
     """
 
     def __init__(self, n_global, rowptr, col, kval, mlump, dt, model='fenton4v', params=None, rank=0, world=1,
-                 group=None, math='fast', device=None, layout='sell'):
+                 group=None, math='fast', device=None, layout='sell', connect=True):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != 'cuda':
             raise L.PdxError('PartitionedExplicitFEM needs a CUDA device: there is no CPU path')
@@ -103,7 +103,8 @@ class PartitionedExplicitFEM:
             raise ValueError('rowptr must describe the %d rows of this rank' % self.nloc)
         self.col_range = (int(col.min()), int(col.max()))
         self.send_lo = self.send_hi = 0
-        if world > 1:
+        self._local = world > 1 and not connect      # ranks sharing one GPU in one process: see connect_local
+        if world > 1 and connect:
             import torch.distributed as dist
             mine = torch.tensor(self.col_range, dtype=torch.int64, device=self.device)
             allr = [torch.zeros_like(mine) for _ in range(world)]
@@ -131,7 +132,7 @@ class PartitionedExplicitFEM:
         self.states = [torch.full((self.nloc,), v, dtype=torch.float32, device=dev) for v in STATE_INIT[self.model_id]]
         self._states_arr = L.ptr_array(self.states)
         self._hdl = None
-        if world > 1:
+        if world > 1 and connect:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
             self.U = [symm.empty((self.n,), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -144,15 +145,33 @@ class PartitionedExplicitFEM:
         for b in self.U:
             b.fill_(-80.0 if self.model_id != L.MODEL_NONE else 0.0)
         self._cur = 0
-        self._primed = world == 1
+        self._primed = world == 1 or self._local
         self.nsteps_done = 0
+
+    @staticmethod
+    def connect_local(ranks):
+        """Wire instances (constructed with connect=False) that live in ONE process on ONE GPU: the neighbours'
+        buffers are plain device pointers and stream order replaces the barrier - the ghost stores fused into
+        the step kernel are exercised on a single-GPU box.  Step the ranks with ``step_local``."""
+        ranks = sorted(ranks, key=lambda f: f.rank)
+        ranges = [f.col_range for f in ranks]
+        for f in ranks:
+            f.send_lo, f.send_hi = plan_exchange(f.blocks, ranges, f.rank)
+            f._peer_lo = [ranks[f.rank - 1].U[b].data_ptr() if f.rank > 0 else None for b in range(2)]
+            f._peer_hi = [ranks[f.rank + 1].U[b].data_ptr() if f.rank < f.world - 1 else None for b in range(2)]
+
+    @staticmethod
+    def step_local(ranks, nsteps=1):
+        for _ in range(nsteps):
+            for f in ranks:             # same stream: every rank's step k completes before any rank's step k+1
+                f.step(1)
 
     # ---- data -------------------------------------------------------------------------------
     def set_global_U(self, U):
         """Install a global potential (host array): own rows and ghost columns become valid."""
         t = torch.from_numpy(np.ascontiguousarray(U, dtype=np.float32).reshape(-1)).to(self.device)
         self.U[self._cur].copy_(t)
-        self._primed = self.world == 1
+        self._primed = self.world == 1 or self._local
 
     def current_U(self):
         return self.U[self._cur]
@@ -178,7 +197,7 @@ class PartitionedExplicitFEM:
                 L.ptr(self.kval), L.ptr(self.mlinv), L.ptr(self.U[i]), L.ptr(self.U[o]), self._states_arr, L.ptr(I0),
                 dt32, self.send_lo, C.c_void_p(self._peer_lo[o]), self.send_hi, C.c_void_p(self._peer_hi[o]),
                 L.stream_ptr()))
-            if self.world > 1:
+            if self.world > 1 and not self._local:
                 self._hdl[0].barrier(channel=0)
             self._cur = o
         self.nsteps_done += nsteps

@@ -103,3 +103,34 @@ def test_partitioned_ranks_match_single_rank_bitwise(cuda, world):
     for rank, lo, U, V in got:
         assert np.array_equal(U, Uref[lo:lo + U.shape[0]])
         assert np.array_equal(V, Vref[lo:lo + V.shape[0]])
+
+
+@pytest.mark.parametrize('world,layout', [(2, 'sell'), (3, 'sell'), (3, 'csr')])
+def test_ranks_sharing_one_gpu_match_single_rank_bitwise(cuda, world, layout):
+    """The ghost stores fused into the explicit step kernel on a ONE-GPU box: the row blocks live in one process and
+    store their edge rows into each other's buffers through plain device pointers (PartitionedExplicitFEM.connect_local)."""
+    from pdensorflow_b200.fem_dist import PartitionedExplicitFEM, row_blocks
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    nx, ny, nz = DIMS
+    n = nx * ny * nz
+    nsteps = 40
+    ranks = []
+    for r, (lo, hi) in enumerate(row_blocks(n, world)):
+        rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA, lo, hi)
+        ranks.append(PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=r, world=world,
+                                            layout=layout, connect=False))
+    PartitionedExplicitFEM.connect_local(ranks)
+    for f in ranks:
+        assert (f.send_lo > 0) == (f.rank > 0) and (f.send_hi > 0) == (f.rank < world - 1)
+        f.set_global_U(_initial(n, DIMS))
+    PartitionedExplicitFEM.step_local(ranks, nsteps)
+    torch.cuda.synchronize()
+    rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA)
+    ref = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', layout=layout)
+    ref.set_global_U(_initial(n, DIMS))
+    ref.step(nsteps)
+    Uref, Vref = ref.current_U().cpu().numpy(), ref.states[0].cpu().numpy()
+    assert Uref.max() > 0.0
+    for f in ranks:
+        assert np.array_equal(f.owned_U().cpu().numpy(), Uref[f.lo:f.hi])
+        assert np.array_equal(f.states[0].cpu().numpy(), Vref[f.lo:f.hi])
