@@ -44,6 +44,7 @@ class ConjGrad:
         self._handle = None
         self._handle_key = None
         self._part = None                 # (handle, workspace, sell arrays) of the large-system path
+        self._Mass = None                 # MASS on A's pattern: lets the large-system kernel form b = MASS*rhs0 itself
         self._info = None
         self._info_host = None
 
@@ -77,6 +78,27 @@ class ConjGrad:
             raise L.PdxError('ConjGrad.set_matrix takes a gpuSolve.matrices.CSRMatrix')
         self._A = Amat
         self._release()
+
+    def fuse_mass(self, Mmat):
+        """(not in the reference) Give the solver the MASS matrix of (MASS + dt*STIFFNESS) U1 = MASS*RHS0: above
+        SELL_MIN_ROWS rows ``solve_from_rhs0`` then forms the right-hand side inside the solve kernel - one launch
+        and one pass over the matrix less per time step."""
+        if self._A is not None and (Mmat.nnz != self._A.nnz or not np.array_equal(Mmat.col, self._A.col)):
+            raise L.PdxError('ConjGrad.fuse_mass: MASS must share the pattern of the system matrix')
+        self._Mass = Mmat
+        self._release()
+
+    def fused_mass_ready(self):
+        return self._Mass is not None and self._A is not None and self._A.n >= SELL_MIN_ROWS
+
+    def solve_from_rhs0(self, rhs0, x):
+        """A x = MASS*rhs0, x holds the guess and receives the solution (large-system path only)."""
+        self._ensure_handle()
+        if self._part is None or self._Mass is None:
+            raise L.PdxError('ConjGrad.solve_from_rhs0 needs fuse_mass() and a system above SELL_MIN_ROWS rows')
+        L.check(L.lib().pdx_pcg_part_solve(self._part[0], None, L.ptr(rhs0), L.ptr(x), int(self._maxiter), float(self._toll),
+                                           int(self._check_every), L.ptr(self._info), L.stream_ptr()))
+        self._X = x
 
     def set_RHS(self, RHS):
         RHS = L.require_cuda(B.as_tensor(RHS), 'RHS')
@@ -160,11 +182,14 @@ class ConjGrad:
                 sp, scol, sval = csr_to_sell32(self._A.rowptr, self._A.col, self._A.val)
                 dev = rp.device
                 arrs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sp, scol, sval)]
+                if self._Mass is not None:
+                    arrs.append(torch.from_numpy(csr_to_sell32(self._Mass.rowptr, self._Mass.col, self._Mass.val)[2]).to(dev))
                 ws = torch.zeros(int(L.lib().pdx_pcg_part_workspace_bytes(self._A.n)), dtype=torch.uint8, device=dev)
                 d = L.PcgPartDesc()
                 d.n_local, d.rank, d.world, d.sell = self._A.n, 0, 1, 1
                 d.lower_window_index = d.upper_window_index = -1
-                d.rowptr, d.col, d.aval = (a.data_ptr() for a in arrs)
+                d.rowptr, d.col, d.aval = (a.data_ptr() for a in arrs[:3])
+                d.mval = arrs[3].data_ptr() if self._Mass is not None else None
                 d.minv = None if minv is None else minv.data_ptr()
                 peers = (C.c_void_p * 1)(ws.data_ptr())
                 L.check(L.lib().pdx_pcg_part_create(C.byref(d), peers, self._A.n, C.byref(h)))

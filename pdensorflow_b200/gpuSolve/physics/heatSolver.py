@@ -88,6 +88,7 @@ class HeatSolver:
         self._Domain.release_connectivity()
         self._materials.remove_all_element_properties()
         self._Solver.set_matrix(A)
+        self._Solver.fuse_mass(self._MASS)          # large systems: RHS = MASS*RHS0 is formed inside the solve kernel
         I, J, V = A.coo()
         self._Precond.build_preconditioner(I, J, V, A.n)
         self._Solver.set_precond(self._Precond)
@@ -137,9 +138,16 @@ class HeatSolver:
         """Implicit Euler solve for the heat equation (heatSolver.py:127-135)."""
         rhs0, rhs = self._work()
         torch.add(U, I0, alpha=float(np.float32(self._dt)), out=rhs0)
-        self._MASS.matvec(rhs0, out=rhs)
+        return self._solve_from_rhs0(U, rhs0, rhs)
+
+    def _solve_from_rhs0(self, U, rhs0, rhs):
+        """(MASS + dt*STIFFNESS) U1 = MASS*RHS0 from the guess U."""
         self._Solver.set_X0(U)
-        self._Solver.solve_inplace(rhs, self._Solver.X())
+        if self._Solver.fused_mass_ready():
+            self._Solver.solve_from_rhs0(rhs0, self._Solver.X())
+        else:
+            self._MASS.matvec(rhs0, out=rhs)
+            self._Solver.solve_inplace(rhs, self._Solver.X())
         return self._Solver.X()
 
     def _compute_forcing(self, ctime):

@@ -101,10 +101,7 @@ class MonodomainSolver(HeatSolver):
             L.check(L.lib().pdx_ionic_lut_step(C.byref(m.lut_desc()), U.numel(), L.ptr(U),
                                                L.ptr_array(states, L.LUT_MAX_STATES), None, L.ptr(I0), L.ptr(rhs0),
                                                L.stream_ptr()))
-            self._MASS.matvec(rhs0, out=rhs)
-            self._Solver.set_X0(U)
-            self._Solver.solve_inplace(rhs, self._Solver.X())
-            return self._Solver.X()
+            return self._solve_from_rhs0(U, rhs0, rhs)
         params, parr, keep = m._param_block(U.numel())
         if self._explicit_lumped:
             if parr is not None:
@@ -125,10 +122,7 @@ class MonodomainSolver(HeatSolver):
         L.check(L.lib().pdx_ionic_step(m._MODEL_ID, math, params, parr, U.numel(), L.ptr(U), L.ptr_array(states),
                                        None, dt32, L.ptr(I0), L.ptr(rhs0), L.stream_ptr()))
         del keep
-        self._MASS.matvec(rhs0, out=rhs)                                   # RHS = MASS . RHS0
-        self._Solver.set_X0(U)
-        self._Solver.solve_inplace(rhs, self._Solver.X())
-        return self._Solver.X()
+        return self._solve_from_rhs0(U, rhs0, rhs)                         # RHS = MASS . RHS0, then PCG
 
     # ---- accessors ----------------------------------------------------------
     def ionic_model(self):

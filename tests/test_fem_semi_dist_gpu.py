@@ -247,3 +247,35 @@ def test_conjgrad_takes_the_sell_path_for_large_systems(cuda):
     xo, nit_o, _ = ofem.pcg(rp, ci, val, minv, b, np.zeros(n, np.float32), 2000, toll)
     assert abs(cg.niters() - nit_o) <= 5
     assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-4
+
+
+def test_monodomain_solver_large_mesh_fuses_the_mass_product(cuda, monkeypatch):
+    """Above SELL_MIN_ROWS rows MonodomainSolver.solve_step = ionic kernel + ONE solve kernel that forms MASS*RHS0
+    itself (SELL-32); it must step like the small-system path (MASS SpMV + CSR PCG) on the same mesh."""
+    from test_fem_gpu import _square
+    from pdensorflow_b200.gpuSolve.ionic import Fenton4v
+    from pdensorflow_b200.gpuSolve.linearsolvers import conjgrad as cgmod
+    from pdensorflow_b200.gpuSolve.physics import MonodomainSolver
+    P, E, F = _square(320)                                   # 102 400 nodes
+    sig = {1: 1e-3, 2: 1e-3, 3: 1e-3, 4: 1e-3}
+    out, fused = [], []
+    for min_rows in (10 ** 9, cgmod.SELL_MIN_ROWS):
+        monkeypatch.setattr(cgmod, 'SELL_MIN_ROWS', min_rows)
+        model = MonodomainSolver(Fenton4v(dt=0.1), {'use_renumbering': True, 'dt': 0.1, 'dt_per_plot': 10, 'Tend': 100})
+        model.domain().set_mesh(P, E, F)
+        model.add_element_material_property('sigma_l', 'region', sig)
+        model.add_element_material_property('sigma_t', 'region', sig)
+        model.assign_nodal_properties()
+        model.assemble_matrices()
+        model.set_initial_condition()
+        model.add_stimulus(P[:, 0] < 0.05 * P[:, 0].max(), {'tstart': 0.0, 'nstim': 1, 'period': 100, 'duration': 0.4, 'intensity': 60.0})
+        model.solver().set_maxiter(200)
+        model.finalize_for_run()
+        t = 0.0
+        for _ in range(20):
+            t += 0.1
+            model.step(t)
+        out.append(model.U().cpu().numpy().ravel())
+        fused.append(model.solver().fused_mass_ready())
+    assert fused == [False, True] and out[0].max() > -70.0
+    assert np.linalg.norm(out[0] - out[1]) <= TOL_CG * np.linalg.norm(out[0])
