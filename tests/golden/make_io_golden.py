@@ -81,8 +81,41 @@ def main():
         out['leftovers'] = np.array(sorted(f for f in os.listdir('.') if '__chunk_' in f) or [''])
     finally:
         os.chdir(cwd)
+    out.update(domain_golden())
     np.savez_compressed(os.path.join(HERE, 'ref_io.npz'), **out)
     print({k: (v.shape, str(v.dtype)) for k, v in out.items()})
+
+
+
+def domain_golden():
+    """Domain3D of the reference (entities/domain3D.py) on seeded arrays: the assign_* path of the FD examples
+    (Tests/FD/Fenton_sphere/fenton.py:86-101) and the anisotropic conductivity / fibre-dyadic conventions."""
+    import types
+    # the reference's Domain3D imports its ImageData reader (imageio / nibabel): not needed on the assign path
+    from gpuSolve.entities.domain3D import Domain3D
+    rng = np.random.default_rng(11)
+    W, H, D = 6, 5, 7
+    geo = (rng.uniform(size=(W, H, D)) > 0.3).astype(np.float64)
+    out = {'dom_geo': geo}
+    d = Domain3D({'width': 3, 'height': 4, 'depth': 5, 'dx': 0.5, 'dy': 0.25, 'dz': 2.0})
+    d.load_geometry_file()
+    d.load_conductivity(cond_unif=0.8)
+    out['dom_box_geometry'] = d.geometry()
+    out['dom_box_conductivity'] = d.conductivity()
+    out['dom_box_meta'] = np.array([d.width(), d.height(), d.depth(), d.dx(), d.dy(), d.dz(), float(d.anisotropic())])
+    d = Domain3D({'dx': 1.0})
+    d.assign_geometry(geo.copy())
+    d.assign_conductivity(0.8 * geo)
+    out['dom_iso_conductivity'] = d.conductivity()
+    out['dom_iso_meta'] = np.array([d.width(), d.height(), d.depth(), float(d.anisotropic())])
+    cond4 = rng.uniform(0.1, 1.0, size=(W, H, D, 1))
+    d.assign_conductivity(cond4.copy())
+    out['dom_cond4_in'], out['dom_cond4'] = cond4, d.conductivity()
+    aniso = np.stack([rng.uniform(0.05, 0.2, size=(W, H, D)), rng.uniform(0.5, 1.0, size=(W, H, D))], axis=-1)
+    d.assign_conductivity(aniso.copy())
+    out['dom_aniso_in'], out['dom_aniso'] = aniso, d.conductivity()
+    out['dom_aniso_flag'] = np.array(float(d.anisotropic()))
+    return out
 
 
 if __name__ == '__main__':

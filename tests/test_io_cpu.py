@@ -134,3 +134,47 @@ def test_reader_tolerates_truncated_and_padded_files(tmp_path):
     assert r.nt() == 2 and np.array_equal(r.data(), data[:2]) and r.ndiff() == nx * 2 + 3 - nx * nt
     r.read(extra)
     assert r.nt() == nt and np.array_equal(r.data(), data) and r.ndiff() == 7
+
+
+def test_domain3d_matches_the_reference():
+    """Domain3D (entities/domain3D.py) on the paths the FD examples use: file-less box,
+    assign_geometry / assign_conductivity (isotropic, trailing singleton channel, anisotropic (sigma_t, sigma_l) ->
+    (sigma_t, sigma_l - sigma_t)) - against the reference's own class run from source (ref_io.npz)."""
+    from pdensorflow_b200.gpuSolve.entities import Domain3D
+    d = Domain3D({'width': 3, 'height': 4, 'depth': 5, 'dx': 0.5, 'dy': 0.25, 'dz': 2.0})
+    d.load_geometry_file()
+    d.load_conductivity(cond_unif=0.8)
+    assert np.array_equal(d.geometry(), G['dom_box_geometry']) and np.array_equal(d.conductivity(), G['dom_box_conductivity'])
+    assert np.array_equal([d.width(), d.height(), d.depth(), d.dx(), d.dy(), d.dz(), float(d.anisotropic())], G['dom_box_meta'])
+    geo = G['dom_geo']
+    d = Domain3D({'dx': 1.0})
+    with pytest.raises(SystemExit):
+        d.assign_conductivity(geo)                         # no geometry yet (domain3D.py:148-149)
+    d.assign_geometry(geo.copy())
+    d.assign_conductivity(0.8 * geo)
+    assert np.array_equal(d.conductivity(), G['dom_iso_conductivity'])
+    assert np.array_equal([d.width(), d.height(), d.depth(), float(d.anisotropic())], G['dom_iso_meta'])
+    d.assign_conductivity(G['dom_cond4_in'].copy())
+    assert np.array_equal(d.conductivity(), G['dom_cond4']) and not d.anisotropic()
+    d.assign_conductivity(G['dom_aniso_in'].copy())
+    assert np.array_equal(d.conductivity(), G['dom_aniso']) and d.anisotropic() == bool(G['dom_aniso_flag'])
+
+
+def test_domain3d_voxel_files(tmp_path):
+    from pdensorflow_b200.gpuSolve.entities import Domain3D
+    rng = np.random.default_rng(5)
+    vox = rng.uniform(2.0, 9.0, size=(4, 3, 5))
+    vox[0, 0, 0] = 2.0
+    fib = rng.standard_normal((4, 3, 5, 3))
+    np.save(tmp_path / 'geo.npy', vox)
+    np.save(tmp_path / 'fib.npy', fib)
+    d = Domain3D()
+    d.load_geometry_file(str(tmp_path / 'geo.npy'), threshold=0.5)
+    unit = (vox - vox.min()) / (vox.max() - vox.min())
+    assert np.array_equal(d.geometry(), (unit > 0.5).astype(float)) and (d.width(), d.height(), d.depth()) == (4, 3, 5)
+    d.load_fiber_direction(str(tmp_path / 'fib.npy'))
+    T = d.fibtensor()
+    assert T.shape == (4, 3, 5, 6)
+    assert np.array_equal(T[..., 1], fib[..., 0] * fib[..., 1]) and np.array_equal(T[..., 5], fib[..., 2] ** 2)
+    with pytest.raises(NotImplementedError):
+        Domain3D().load_geometry_file('atria.png', 10, 10)
