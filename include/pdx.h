@@ -243,6 +243,11 @@ int  pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const 
 void pdx_pcg_destroy(pdx_pcg* s);
 int  pdx_pcg_solve(pdx_pcg* s, const float* b, float* x, int maxiter, double toll,
                    int check_every, int32_t* info /* device, 4 words */, void* stream);
+/* The same solve with the right-hand side of MonodomainSolver.solve_step / HeatSolver.solve_step formed inside
+ * the kernel: b = MASS * rhs0 (monodomainSolver.py:104, heatSolver.py:132), mval = MASS values on the system
+ * matrix' pattern.  One launch and one vector round trip less per time step. */
+int  pdx_pcg_solve_rhs0(pdx_pcg* s, const float* mval, const float* rhs0, float* x, int maxiter, double toll,
+                        int check_every, int32_t* info /* device, 4 words */, void* stream);
 
 /* Explicit mass-lumped FEM step named by the north star (no reference implementation;
  * SURVEY.md section 8a row E): U1 = U + dt*(dU + I0) - dt * mlinv * (K U), fused with the

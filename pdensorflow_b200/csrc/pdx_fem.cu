@@ -37,7 +37,9 @@ struct PcgArgs {
     const int32_t* col;
     const float* val;
     const float* minv;      // may be null
-    const float* b;
+    const float* b;         // right-hand side, or null: b = M * rhs0 with M = mval on A's pattern
+    const float* mval;
+    const float* rhs0;
     float* x;
     float *r, *p, *q;       // work vectors
     float* part;            // 3 * gridDim.x partial sums
@@ -65,10 +67,13 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
     for (int row = gid; row < nround; row += ngroups) {
         {
             const bool valid = row < a.n;
-            const float ax = row_dot<G>(a.col, a.val, a.x, valid ? a.rowptr[row] : 0, valid ? a.rowptr[row + 1] : 0,
-                                        sub, true);
+            const int beg = valid ? a.rowptr[row] : 0, end = valid ? a.rowptr[row + 1] : 0;
+            const float ax = row_dot<G>(a.col, a.val, a.x, beg, end, sub, true);
+            float bv = 0.0f;
+            if (!a.b) bv = row_dot<G>(a.col, a.mval, a.rhs0, beg, end, sub, true);     // uniform branch: RHS = MASS*RHS0
             if (valid && sub == 0) {
-                const float r = __fsub_rn(a.b[row], ax);
+                if (a.b) bv = a.b[row];
+                const float r = __fsub_rn(bv, ax);
                 const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
                 __stcg(a.r + row, r);
                 __stcg(a.p + row, z);
@@ -338,12 +343,26 @@ void pdx_pcg_destroy(pdx_pcg* s) {
     delete s;
 }
 
+static int pcg_launch(pdx_pcg* s, const float* b, const float* mval, const float* rhs0, float* x, int maxiter, double toll,
+                      int check_every, int32_t* info, void* stream);
+
 int pdx_pcg_solve(pdx_pcg* s, const float* b, float* x, int maxiter, double toll, int check_every, int32_t* info,
                   void* stream) {
     if (!s || !b || !x || maxiter < 0) { set_error("pdx_pcg_solve: bad arguments"); return 1; }
+    return pcg_launch(s, b, nullptr, nullptr, x, maxiter, toll, check_every, info, stream);
+}
+
+int pdx_pcg_solve_rhs0(pdx_pcg* s, const float* mval, const float* rhs0, float* x, int maxiter, double toll,
+                       int check_every, int32_t* info, void* stream) {
+    if (!s || !mval || !rhs0 || !x || maxiter < 0) { set_error("pdx_pcg_solve_rhs0: bad arguments"); return 1; }
+    return pcg_launch(s, nullptr, mval, rhs0, x, maxiter, toll, check_every, info, stream);
+}
+
+static int pcg_launch(pdx_pcg* s, const float* b, const float* mval, const float* rhs0, float* x, int maxiter, double toll,
+                      int check_every, int32_t* info, void* stream) {
     PcgArgs a{};
     a.n = s->n; a.rowptr = s->rowptr; a.col = s->col; a.val = s->val; a.minv = s->minv;
-    a.b = b; a.x = x;
+    a.b = b; a.mval = mval; a.rhs0 = rhs0; a.x = x;
     a.r = s->work; a.p = s->work + s->n; a.q = s->work + 2 * (size_t)s->n;
     a.part = s->part;
     a.maxiter = maxiter;

@@ -80,24 +80,29 @@ class ConjGrad:
         self._release()
 
     def fuse_mass(self, Mmat):
-        """(not in the reference) Give the solver the MASS matrix of (MASS + dt*STIFFNESS) U1 = MASS*RHS0: above
-        SELL_MIN_ROWS rows ``solve_from_rhs0`` then forms the right-hand side inside the solve kernel - one launch
-        and one pass over the matrix less per time step."""
+        """(not in the reference) Give the solver the MASS matrix of (MASS + dt*STIFFNESS) U1 = MASS*RHS0:
+        ``solve_from_rhs0`` then forms the right-hand side inside the solve kernel - one launch and one vector
+        round trip less per time step."""
         if self._A is not None and (Mmat.nnz != self._A.nnz or not np.array_equal(Mmat.col, self._A.col)):
             raise L.PdxError('ConjGrad.fuse_mass: MASS must share the pattern of the system matrix')
         self._Mass = Mmat
         self._release()
 
     def fused_mass_ready(self):
-        return self._Mass is not None and self._A is not None and self._A.n >= SELL_MIN_ROWS
+        return self._Mass is not None and self._A is not None
 
     def solve_from_rhs0(self, rhs0, x):
-        """A x = MASS*rhs0, x holds the guess and receives the solution (large-system path only)."""
+        """A x = MASS*rhs0, x holds the guess and receives the solution."""
         self._ensure_handle()
-        if self._part is None or self._Mass is None:
-            raise L.PdxError('ConjGrad.solve_from_rhs0 needs fuse_mass() and a system above SELL_MIN_ROWS rows')
-        L.check(L.lib().pdx_pcg_part_solve(self._part[0], None, L.ptr(rhs0), L.ptr(x), int(self._maxiter), float(self._toll),
-                                           int(self._check_every), L.ptr(self._info), L.stream_ptr()))
+        if self._Mass is None:
+            raise L.PdxError('ConjGrad.solve_from_rhs0 needs fuse_mass()')
+        if self._part is not None:
+            L.check(L.lib().pdx_pcg_part_solve(self._part[0], None, L.ptr(rhs0), L.ptr(x), int(self._maxiter),
+                                               float(self._toll), int(self._check_every), L.ptr(self._info), L.stream_ptr()))
+        else:
+            mval = self._Mass.device_arrays()[2]
+            L.check(L.lib().pdx_pcg_solve_rhs0(self._handle, L.ptr(mval), L.ptr(rhs0), L.ptr(x), int(self._maxiter),
+                                               float(self._toll), int(self._check_every), L.ptr(self._info), L.stream_ptr()))
         self._X = x
 
     def set_RHS(self, RHS):

@@ -276,6 +276,6 @@ def test_monodomain_solver_large_mesh_fuses_the_mass_product(cuda, monkeypatch):
             t += 0.1
             model.step(t)
         out.append(model.U().cpu().numpy().ravel())
-        fused.append(model.solver().fused_mass_ready())
+        fused.append(model.solver()._part is not None)
     assert fused == [False, True] and out[0].max() > -70.0
     assert np.linalg.norm(out[0] - out[1]) <= TOL_CG * np.linalg.norm(out[0])
