@@ -223,6 +223,8 @@ int pdx_ionic_step(int model, int math_mode, const float* params,
  * U = mask ? max(U, intensity*mask) : U, mask as produced by Stimulus.set_stimregion
  * (force_terms/stimulus.py:73-80). */
 int pdx_stim_apply(float* U, const float* mask, float intensity, int64_t n, void* stream);
+/* The heat examples' form (Tests/FD/HeatEquation/heat.py:143-144): U = maximum(U, intensity*mask) on EVERY node. */
+int pdx_stim_apply_max(float* U, const float* mask, float intensity, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ FEM path */
 /* y = A x, CSR fp32 / int32 (replaces tf.raw_ops.SparseMatrixMatMul with a [N,1]

@@ -172,7 +172,7 @@ def laplace_heterog_2d(X0, DIFF0, DX, DY):
     return ((e - w) / dxsq + (n - s) / dysq).astype(np.float32)
 
 
-def fd_step(model, U, dt, diff, spacing, DIFF=None, conv=False):
+def fd_step(model, U, dt, diff, spacing, DIFF=None, conv=False, dirichlet=None):
     """One explicit step as the FD examples' ``solve`` writes it.
 
     Homogeneous (Tests/FD/Fenton/fenton.py:90-99):
@@ -182,8 +182,10 @@ def fd_step(model, U, dt, diff, spacing, DIFF=None, conv=False):
     ``model`` is an oracle ionic model (or None for the heat equation,
     Tests/FD/HeatEquation/heat.py:86-94).  ``dt`` and ``diff`` are Python floats: their
     product is formed in float64 and rounded to fp32 where it meets the tensor.
+    ``dirichlet``: constant boundary value of Tests/FD/LaplaceSolver/laplaceSolver.py:44-52,136-141 (U0 = constant pad
+    of the interior instead of the symmetric one).
     """
-    U0 = enforce_boundary(U)
+    U0 = enforce_boundary(U) if dirichlet is None else enforce_boundary_dirichlet(U, dirichlet)
     three_d = U.ndim == 3
     if DIFF is None:
         if three_d:
@@ -205,6 +207,11 @@ def fd_step(model, U, dt, diff, spacing, DIFF=None, conv=False):
 def apply_stimulus(U, stim):
     """Tests/FD/Fenton/fenton.py:154-156: U = where(bool(stim), max(U, stim), U)."""
     return np.where(stim.astype(bool), np.maximum(U, stim), U).astype(np.float32)
+
+
+def apply_stimulus_max(U, stim):
+    """Tests/FD/HeatEquation/heat.py:143-144: U = maximum(U, s2()) on every node."""
+    return np.maximum(U, stim).astype(np.float32)
 
 
 def fd_run(model, U, nsteps, dt, diff, spacing, DIFF=None, conv=False, s2=None, step0=0,

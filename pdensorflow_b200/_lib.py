@@ -87,6 +87,7 @@ _SIGNATURES = {
     'pdx_fd_plan_set_avec': (C.c_int, [_P, _P]),
     'pdx_fd_laplace_aniso': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     'pdx_stim_apply': (C.c_int, [_P, _P, C.c_float, C.c_int64, _P]),
+    'pdx_stim_apply_max': (C.c_int, [_P, _P, C.c_float, C.c_int64, _P]),
     'pdx_csr_spmv': (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P]),
     'pdx_pcg_create': (C.c_int, [C.c_int32, _P, _P, _P, _P, C.POINTER(_P)]),
     'pdx_pcg_destroy': (None, [_P]),

@@ -557,4 +557,10 @@ int pdx_stim_apply(float* U, const float* mask, float intensity, int64_t n, void
     return launch_stim(U, mask, intensity, n, (cudaStream_t)stream);
 }
 
+int pdx_stim_apply_max(float* U, const float* mask, float intensity, int64_t n, void* stream) {
+    if (n < 0 || (n > 0 && (!U || !mask))) { set_error("pdx_stim_apply_max: bad arguments"); return 1; }
+    if (n == 0) return 0;
+    return launch_stim_max(U, mask, intensity, n, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -194,6 +194,22 @@ __global__ void __launch_bounds__(256) stim_kernel(float* U, const float* mask, 
     }
 }
 
+// heat examples: U = maximum(U, intensity*mask) on EVERY node (Tests/FD/HeatEquation/heat.py:143-144)
+__global__ void __launch_bounds__(256) stim_max_kernel(float* U, const float* mask, float intensity, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        U[i] = fmaxf(U[i], __fmul_rn(intensity, mask[i]));
+}
+
+int launch_stim_max(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s) {
+    int64_t nb = (n + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb < 1) nb = 1;
+    stim_max_kernel<<<(unsigned)nb, 256, 0, s>>>(U, mask, intensity, n);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "stim_max_kernel launch");
+}
+
 int launch_stim(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s) {
     int64_t nb = (n + 255) / 256;
     if (nb > 148 * 16) nb = 148 * 16;

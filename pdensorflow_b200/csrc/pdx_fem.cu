@@ -5,6 +5,8 @@
 // physics/monodomainSolver.py:104), ConjGrad._initialize/_iterate/solve
 // (conjgrad.py:172-203,257-312), JacobiPrecond.solve_precond_system (jacobi_precond.py:35-41).
 #include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
 #include <new>
 #include "pdx_internal.h"
 #include "pdx_fem_dev.cuh"
@@ -327,6 +329,10 @@ int pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const f
     long long nb = want < cap ? want : cap;
     if (nb < 1) nb = 1;
     if (nb > sms && (long long)n * s->G <= (long long)sms * 256 * 8) nb = sms;
+    {   // PDX_PCG_BLOCKS=<n>: grid size override for tuning runs (clamped to what can be co-resident)
+        const char* e = std::getenv("PDX_PCG_BLOCKS");
+        if (e && std::atoi(e) > 0) nb = std::min<long long>(std::atoi(e), (long long)sms * per_sm);
+    }
     s->nblocks = (int)nb;
     if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 3 * (size_t)n), "cudaMalloc(pcg work)")) { delete s; return 1; }
     if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 3 * (size_t)s->nblocks), "cudaMalloc(pcg partials)")) {

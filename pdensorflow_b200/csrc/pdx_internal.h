@@ -67,6 +67,7 @@ int launch_enforce_boundary(const FdArgs& a, cudaStream_t s);
 int launch_ionic(int model, int math, const float* params, const float* const* parr, int64_t n, const float* U,
                  float* const* states, float* dU, float dt, const float* I0, float* rhs0, cudaStream_t s);
 int launch_stim(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s);
+int launch_stim_max(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s);
 int launch_fd_laplace_aniso(const FdArgs& a, cudaStream_t s);
 int lut_model_num_consts(int model);
 // one translation unit per arithmetic policy (pdx_ionic_lut.cu is compiled twice)

@@ -99,10 +99,12 @@ class FDStepper:
               arrays the instance owns
     lap:      'homog' | 'conv' | 'heterog' (DIFF [W,H,D] carries the diffusivity) |
               'aniso' (DIFF [W,H,D,2] and AVEC [W,H,D,6] as laplace_heterog_aniso takes them)
+    dirichlet: None = the examples' no-flux boundary (symmetric pad); a float = the constant boundary value of
+              Tests/FD/LaplaceSolver/laplaceSolver.py:44-52 (constant pad of the interior)
     """
 
     def __init__(self, shape, spacing, dt, diff=1.0, model='fenton4v', params=None, lap='homog', DIFF=None,
-                 math='fast', kernel='auto', part=None, device=None, x_chunk=0, AVEC=None, buffers=None):
+                 math='fast', kernel='auto', part=None, device=None, x_chunk=0, AVEC=None, buffers=None, dirichlet=None):
         self.device = torch.device('cuda' if device is None else device)
         if self.device.type != 'cuda':
             raise L.PdxError('FDStepper needs a CUDA device: there is no CPU path')
@@ -143,6 +145,8 @@ class FDStepper:
         d.lap_kind, d.model = self.lap_id, self.model_id
         d.math_mode, d.kernel = _MATH_IDS[math], _KERNEL_IDS[kernel]
         d.x_chunk = int(x_chunk)
+        if dirichlet is not None:
+            d.dirichlet, d.dirichlet_value = 1, float(np.float32(dirichlet))
         if self.model_id != L.MODEL_NONE and not self.is_lut:
             p = L.default_params(self.model_id) if params is None else list(params)
             for i, v in enumerate(p):
@@ -285,11 +289,12 @@ class FDStepper:
         if rem:
             self.step(rem)
 
-    def apply_stimulus(self, mask, intensity, stream=None):
-        """U = where(mask, max(U, intensity*mask), U): Tests/FD/Fenton/fenton.py:154-156."""
+    def apply_stimulus(self, mask, intensity, stream=None, everywhere=False):
+        """U = where(mask, max(U, intensity*mask), U): Tests/FD/Fenton/fenton.py:154-156; ``everywhere=True`` is the
+        heat examples' U = maximum(U, intensity*mask) on every node (Tests/FD/HeatEquation/heat.py:143-144)."""
         U = self.current_U()
-        L.check(L.lib().pdx_stim_apply(L.ptr(U), L.ptr(mask), float(np.float32(intensity)), U.numel(),
-                                       L.stream_ptr(stream)))
+        fn = L.lib().pdx_stim_apply_max if everywhere else L.lib().pdx_stim_apply
+        L.check(fn(L.ptr(U), L.ptr(mask), float(np.float32(intensity)), U.numel(), L.stream_ptr(stream)))
 
     def launches(self):
         """Kernel launches issued for this stepper: direct ones plus graph-replayed nodes

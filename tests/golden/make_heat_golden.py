@@ -1,0 +1,72 @@
+"""Generate tests/golden/ref_heat.npz by EXECUTING THE REFERENCE'S heat / Laplace examples (build container only).
+
+    python tests/golden/make_heat_golden.py
+
+Tests/FD/HeatEquation/heat.py (run() end to end: Neumann boundary, homogeneous and conv Laplacian, the S2 source applied
+as U = max(U, s2())) and the step of Tests/FD/LaplaceSolver/laplaceSolver.py (Dirichlet constant pad + heterogeneous
+operator, laplaceSolver.py:44-52,136-141) are imported unmodified from /root/reference over tests/golden/tf_facade.py.
+LaplaceSolver.__init__ reads a PNG through imageio (absent here), so the instance is created without it and given a
+seeded conductivity field; solve() is the reference's own.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import tf_facade as tf  # noqa: E402
+
+tf.install()
+from make_ref_golden import load_example  # noqa: E402
+
+
+class Capture:
+    def __init__(self):
+        self.frames = []
+
+    def imshow(self, U):
+        self.frames.append(np.array(U))
+
+    def wait(self):
+        pass
+
+
+def main():
+    out = {}
+    ex = load_example('Tests/FD/HeatEquation/heat.py', 'ref_fd_heat_example')
+    for tag, convl, shape3, spac in (('heat', False, (10, 12, 8), (1.0, 0.8, 1.25)), ('heatconv', True, (9, 8, 12), (1.0, 1.0, 1.0))):
+        cfg = {'width': shape3[0], 'height': shape3[1], 'depth': shape3[2], 'dx': spac[0], 'dy': spac[1], 'dz': spac[2],
+               'dt': 0.05, 'dt_per_plot': 10, 'diff': 0.8, 'samples': 60, 's2_time': 1.5, 'convl': convl}
+        model = ex.HeatEquation(cfg)
+        cap = Capture()
+        model.run(cap)
+        out[tag + '_cfg'] = np.array([cfg[k] for k in ('width', 'height', 'depth', 'dx', 'dy', 'dz', 'dt', 'dt_per_plot', 'diff',
+                                                       'samples', 's2_time')], dtype=np.float64)
+        out[tag + '_frames'] = np.stack(cap.frames)
+        print(tag, len(cap.frames), cap.frames[-1].min(), cap.frames[-1].max())
+    ls_mod = load_example('Tests/FD/LaplaceSolver/laplaceSolver.py', 'ref_fd_laplace_example')
+    rng = np.random.default_rng(12)
+    shp = (9, 11, 10)
+    cond = (1.0 * (rng.uniform(size=shp) > 0.35)).astype(np.float32)           # 0 inside the "anatomy", diff outside
+    ls = ls_mod.LaplaceSolver.__new__(ls_mod.LaplaceSolver)
+    ls.dt, ls.walltmp = 0.1, 10
+    ls.conductivity = tf.constant(cond, dtype=np.float32)
+    ls.DX, ls.DY, ls.DZ = (tf.constant(v, dtype=np.float32) for v in (1.0, 1.0, 1.0))
+    U = ls_mod.enforce_boundary(tf.Variable(np.zeros(shp, np.float32)))          # default cval = 10.0 (laplaceSolver.py:160)
+    frames = [np.array(U)]
+    for _ in range(30):
+        U = ls.solve(U)
+        frames.append(np.array(U))
+    out['lapsolve_cond'] = cond
+    out['lapsolve_frames'] = np.stack(frames)[[0, 1, 2, 10, 30]]
+    out['lapsolve_cfg'] = np.array([0.1, 10.0, 1.0, 1.0, 1.0])
+    rngX = rng.uniform(-3.0, 12.0, size=shp).astype(np.float32)
+    out['lapsolve_eb_in'] = rngX
+    out['lapsolve_eb_out'] = np.array(ls_mod.enforce_boundary(tf.constant(rngX), 2.5))
+    np.savez_compressed(os.path.join(HERE, 'ref_heat.npz'), **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    main()

@@ -242,6 +242,45 @@ def test_fd_example_end_to_end_bit_exact(tag, conv):
     assert_same(m._S_state, g[tag + '_S'], 'S')
 
 
+@pytest.mark.parametrize('tag,conv', [('heat', False), ('heatconv', True)])
+def test_heat_example_end_to_end_bit_exact(tag, conv):
+    """Tests/FD/HeatEquation/heat.py run(): Neumann boundary, U0 + (diff*dt)*lap(U0), S2 applied as max(U, s2())."""
+    g = gold('ref_heat.npz')
+    W, H, D, dx, dy, dz, dt, per_plot, diff, samples, s2_time = (float(v) for v in g[tag + '_cfg'])
+    shape = (int(W), int(H), int(D))
+    U = np.zeros(shape, dtype=np.float32)
+    U[0:2] = 1.0
+    s2_init = np.zeros(shape, dtype=np.float32)
+    s2_init[:shape[0] // 2, :shape[1] // 2, :] = 1.0
+    s2 = Stimulus({'tstart': s2_time, 'nstim': 1, 'period': 800, 'duration': dt, 'dt': dt, 'intensity': 1.0})
+    s2.set_stimregion(s2_init)
+    frames = [U.copy()]
+    fired = 0
+    for i in range(int(samples)):
+        U = ofd.fd_step(None, U, dt, diff, (dx, dy, dz), conv=conv)
+        if s2.stimulate_tissue_timestep(i, dt):
+            U = ofd.apply_stimulus_max(U, s2())
+            fired += 1
+        if i % int(per_plot) == 0:
+            frames.append(U.copy())
+    assert fired == 1
+    assert_same(np.stack(frames), g[tag + '_frames'], tag + ' frames')
+
+
+def test_laplace_solver_step_bit_exact():
+    """Tests/FD/LaplaceSolver/laplaceSolver.py: Dirichlet constant pad + heterogeneous operator, U0 + dt*lap_D(U0)."""
+    g = gold('ref_heat.npz')
+    assert_same(ofd.enforce_boundary_dirichlet(g['lapsolve_eb_in'], 2.5), g['lapsolve_eb_out'], 'enforce_boundary(cval)')
+    dt, wall, dx, dy, dz = (float(v) for v in g['lapsolve_cfg'])
+    cond = g['lapsolve_cond']
+    U = ofd.enforce_boundary_dirichlet(np.zeros(cond.shape, np.float32), 10.0)
+    frames = [U.copy()]
+    for _ in range(30):
+        U = ofd.fd_step(None, U, dt, 1.0, (dx, dy, dz), DIFF=cond, dirichlet=wall)
+        frames.append(U.copy())
+    assert_same(np.stack(frames)[[0, 1, 2, 10, 30]], g['lapsolve_frames'], 'LaplaceSolver frames')
+
+
 def test_fd_heterogeneous_step_bit_exact():
     g = gold('ref_fd.npz')
     dx, dy, dz = (float(v) for v in g['fdhet_spacing'])

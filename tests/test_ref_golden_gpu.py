@@ -202,6 +202,60 @@ def test_fd_heterogeneous_steps_vs_reference_source(cuda):
         assert rel_l2(host(st.states[0]), g['fdhet_V40']) <= tol
 
 
+@pytest.mark.parametrize('tag,conv', [('heat', False), ('heatconv', True)])
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_heat_example_end_to_end_vs_reference_source(cuda, tag, conv, math):
+    """Tests/FD/HeatEquation/heat.py run() on the fused kernel without an ionic model: Neumann boundary,
+    U0 + (diff*dt)*lap(U0), the S2 source applied as U = maximum(U, s2()) on every node."""
+    from pdensorflow_b200.fd import FDStepper
+    from pdensorflow_b200.gpuSolve.force_terms import Stimulus
+    g = gold('ref_heat.npz')
+    W, H, D, dx, dy, dz, dt, per_plot, diff, samples, s2_time = (float(v) for v in g[tag + '_cfg'])
+    shape = (int(W), int(H), int(D))
+    U = np.zeros(shape, dtype=np.float32)
+    U[0:2] = 1.0
+    s2_init = np.zeros(shape, dtype=np.float32)
+    s2_init[:shape[0] // 2, :shape[1] // 2, :] = 1.0
+    st = FDStepper(shape, (dx, dy, dz), dt, diff, model=None, lap='conv' if conv else 'homog', math=math)
+    st.set_U(U)
+    s2 = Stimulus({'tstart': s2_time, 'nstim': 1, 'period': 800, 'duration': dt, 'dt': dt, 'intensity': 1.0})
+    s2.set_stimregion(s2_init)
+    frames = [host(st.U()).copy()]
+    for i in range(int(samples)):
+        st.step(1)
+        if s2.stimulate_tissue_timestep(i, dt):
+            st.apply_stimulus(s2.get_stimregion(), s2.intensity(), everywhere=True)
+        if i % int(per_plot) == 0:
+            frames.append(host(st.U()).copy())
+    ref = g[tag + '_frames']
+    for k in range(ref.shape[0]):
+        assert rel_l2(frames[k], ref[k]) <= (1e-6 if math == 'exact' else 1e-5), (k, rel_l2(frames[k], ref[k]))
+    if math == 'exact':
+        assert np.abs(np.stack(frames) - ref).max() <= 1e-6   # values in [0, 1]: a few ulp at most
+
+
+def test_laplace_solver_step_vs_reference_source(cuda):
+    """Tests/FD/LaplaceSolver/laplaceSolver.py solve(): Dirichlet constant pad (walltmp) + heterogeneous operator."""
+    from pdensorflow_b200.fd import FDStepper
+    from pdensorflow_b200.gpuSolve.fd import enforce_boundary
+    g = gold('ref_heat.npz')
+    X = torch.from_numpy(g['lapsolve_eb_in']).cuda()
+    assert np.array_equal(host(enforce_boundary(X, dirichlet_value=2.5)), g['lapsolve_eb_out'])
+    dt, wall, dx, dy, dz = (float(v) for v in g['lapsolve_cfg'])
+    cond, ref = g['lapsolve_cond'], g['lapsolve_frames']
+    st = FDStepper(cond.shape, (dx, dy, dz), dt, 1.0, model=None, lap='heterog', DIFF=cond, math='exact', dirichlet=wall)
+    assert st.kernel == 'generic'
+    st.set_U(ref[0])
+    got = {0: host(st.U()).copy()}
+    for n in range(1, 31):
+        st.step(1)
+        if n in (1, 2, 10, 30):
+            got[n] = host(st.U()).copy()
+    for k, n in enumerate((0, 1, 2, 10, 30)):
+        assert rel_l2(got[n], ref[k]) <= 1e-6, (n, rel_l2(got[n], ref[k]))
+    assert ref[4].max() <= 10.0 + 1e-5 and ref[4][1:-1, 1:-1, 1:-1].max() > 0.5      # the wall temperature diffuses in
+
+
 # ------------------------------------------------------------------------------ fused FD + LUT models
 @pytest.mark.parametrize('tag', ['crn', 'ttp'])
 @pytest.mark.parametrize('lap,math', [('homog', 'exact'), ('heterog', 'exact'), ('homog', 'fast')])
