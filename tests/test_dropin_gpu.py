@@ -179,3 +179,29 @@ def test_stimulus_mirror_timing_equals_oracle(cuda):
     for i in range(2500):
         assert c.stimulate_tissue_timestep(i, 0.1) == d.stimulate_tissue_timestep(i, 0.1)
     assert np.array_equal(a().cpu().numpy(), b())
+
+
+def test_example_scripts_run(cuda, tmp_path, monkeypatch):
+    """examples/fd_fenton.py and examples/fem_fenton.py (the reference's two flagship examples on the drop-in package)
+    run end to end on small sizes and leave readable result files."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, 'examples', name + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    monkeypatch.setattr(sys, 'argv', ['fd_fenton.py', '--size', '24', '--samples', '60', '--out', str(tmp_path / 'cube3D')])
+    load('fd_fenton').main()
+    cube = np.load(str(tmp_path / 'cube3D_24_24_24.npy'))
+    assert cube.shape == (7, 24, 24, 24) and np.isfinite(cube).all() and cube[-1].max() > 0.0
+    monkeypatch.setattr(sys, 'argv', ['fem_fenton.py', '--n', '31', '--tend', '4', '--out', str(tmp_path / 'sq.igb')])
+    load('fem_fenton').main()
+    from pdensorflow_b200.gpuSolve.IO.readers import IGBReader
+    r = IGBReader()
+    r.read(str(tmp_path / 'sq.igb'))
+    assert r.nx() == 31 * 31 and r.nt() == 4 and r.ndiff() == 0 and r.data().max() > 0.0
