@@ -64,6 +64,21 @@ def main():
     rngX = rng.uniform(-3.0, 12.0, size=shp).astype(np.float32)
     out['lapsolve_eb_in'] = rngX
     out['lapsolve_eb_out'] = np.array(ls_mod.enforce_boundary(tf.constant(rngX), 2.5))
+    # ---- Tests/FD/Fenton_sphere/fenton.py end to end: Domain3D geometry mask, DIFF = diff*mask (0 outside the tissue),
+    # heterogeneous operator, masked initial condition / stimulus / frames ------------------------------------------
+    sp = load_example('Tests/FD/Fenton_sphere/fenton.py', 'ref_fd_sphere_example')
+    for tag, hole, cyl in (('sphere_hole', True, True), ('sphere_ball', False, False)):
+        cfg = {'width': 24, 'height': 24, 'depth': 10, 'radius': 5 if hole else 11, 'hole': hole, 'cylindric': cyl, 'dt': 0.1,
+               'dt_per_plot': 10, 'diff': 0.8, 'samples': 80, 's2_time': 4.0}
+        model = sp.Fenton4vSimple(cfg)
+        cap = Capture()
+        model.run(cap)
+        out[tag + '_cfg'] = np.array([cfg[k] for k in ('width', 'height', 'depth', 'radius', 'dt', 'dt_per_plot', 'diff', 'samples',
+                                                       's2_time')] + [float(hole), float(cyl)], dtype=np.float64)
+        out[tag + '_frames'] = np.stack(cap.frames)
+        out[tag + '_geometry'] = np.asarray(model.domain(), dtype=np.float32)
+        out[tag + '_V'] = model._V_state.numpy()
+        print(tag, len(cap.frames), cap.frames[-1].min(), cap.frames[-1].max(), out[tag + '_geometry'].mean())
     np.savez_compressed(os.path.join(HERE, 'ref_heat.npz'), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -281,6 +281,49 @@ def test_laplace_solver_step_bit_exact():
     assert_same(np.stack(frames)[[0, 1, 2, 10, 30]], g['lapsolve_frames'], 'LaplaceSolver frames')
 
 
+@pytest.mark.parametrize('tag', ['sphere_hole', 'sphere_ball'])
+def test_sphere_example_end_to_end_bit_exact(tag):
+    """Tests/FD/Fenton_sphere/fenton.py run(): geometry mask built as the example builds it and held by the Domain3D
+    MIRROR, DIFF = diff*mask (0 outside the tissue), heterogeneous operator, masked initial condition, masked S2,
+    frames = where(mask, U, -1)."""
+    from pdensorflow_b200.gpuSolve.entities import Domain3D
+    g = gold('ref_heat.npz')
+    W, H, D, radius, dt, per_plot, diff, samples, s2_time, hole, cyl = (float(v) for v in g[tag + '_cfg'])
+    W, H, D, hole, cyl = int(W), int(H), int(D), bool(hole), bool(cyl)
+    dom = Domain3D({'width': W, 'height': H, 'depth': D})
+    c0 = 0.5 * np.array([dom.dx() * W, dom.dy() * H, dom.dz() * D])
+    xx, yy, zz = np.meshgrid(dom.dx() * np.arange(W), dom.dy() * np.arange(H), dom.dz() * np.arange(D))
+    distsq = (xx - c0[0]) ** 2 + (yy - c0[1]) ** 2 + np.float32(not cyl) * (zz - c0[2]) ** 2
+    inside = distsq <= radius * radius
+    vox = (np.logical_not(inside) if hole else inside).astype(np.float32)
+    dom.assign_geometry(vox)
+    dom.assign_conductivity(diff * vox)
+    assert np.array_equal(dom.geometry(), g[tag + '_geometry'])
+    DIFF = dom.conductivity().astype(np.float32)
+    mask = dom.geometry() > 0.0
+    U = np.full((W, H, D), -80.0, dtype=np.float32)
+    s2_init = np.full((W, H, D), -80.0, dtype=np.float32)
+    if hole:
+        U[0:2] = 20.0
+        s2_init[:W // 2, :H // 2, :] = 20.0
+    else:
+        U[W // 2 - 10:W // 2 + 10] = 20.0
+        s2_init[:, H // 2 - 10:H // 2 + 10, :] = 20.0
+    U = np.where(mask, U, np.float32(-80.0)).astype(np.float32)
+    m = oi.Fenton4v()
+    m._dt = dt
+    m.initialize_state_variables(U)
+    s2 = Stimulus({'tstart': s2_time, 'nstim': 1, 'period': 800, 'duration': dt, 'dt': dt, 'intensity': 60.0})
+    s2.set_stimregion(np.where(mask, s2_init, -80.0))
+    frames = [U.copy()]
+    for i in range(int(samples)):
+        U = ofd.fd_run(m, U, 1, dt, 1.0, (dom.dx(), dom.dy(), dom.dz()), DIFF=DIFF, s2=s2, step0=i)
+        if i % int(per_plot) == 0:
+            frames.append(np.where(mask, U, np.float32(-1.0)).astype(np.float32))
+    assert_same(np.stack(frames), g[tag + '_frames'], tag + ' frames')
+    assert_same(m._V_state, g[tag + '_V'], 'V')
+
+
 def test_fd_heterogeneous_step_bit_exact():
     g = gold('ref_fd.npz')
     dx, dy, dz = (float(v) for v in g['fdhet_spacing'])
