@@ -1,5 +1,4 @@
 """ModifiedMS2v - mirror of gpuSolve/ionic/mms2v.py:36-105 (Corrado-Niederer 2016)."""
-import torch
 
 from .ionicmodel import IonicModel
 from .fenton4v import _c, _getter

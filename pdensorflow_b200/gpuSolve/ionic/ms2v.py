@@ -1,5 +1,4 @@
 """MitchellSchaeffer2v - mirror of gpuSolve/ionic/ms2v.py:36-100 (Mitchell-Schaeffer 2003)."""
-import torch
 
 from .ionicmodel import IonicModel
 from .fenton4v import _c, _getter

@@ -14,7 +14,6 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .abstract_precond import AbstractPrecond
 from .. import _backend as B
 from ... import _lib as L
 from ..matrices.globalMatrices import CSRMatrix

@@ -1,7 +1,6 @@
 """JacobiPrecond - mirror of gpuSolve/linearsolvers/jacobi_precond.py:5-41: V = 1/diag(A) (zeros where
 the diagonal is absent); the preconditioned residual z = V*r is fused into libpdx's PCG kernel."""
 import numpy as np
-import torch
 
 from .abstract_precond import AbstractPrecond
 from .. import _backend as B

@@ -9,7 +9,6 @@ once.  The host NumPy path stays the default for small meshes (it is the one pin
 reference's NumPy assembly); ``HeatSolver`` switches to this one above ``DEVICE_ASSEMBLY_MIN_ELEMENTS``
 elements or when cfg ``device_assembly`` is True.
 """
-import ctypes as C
 from time import time
 
 import numpy as np

@@ -11,7 +11,6 @@ import numpy as np
 import torch
 
 from .heatSolver import HeatSolver
-from .. import _backend as B
 from ... import _lib as L
 
 _IONIC_STATE_ATTRS = ('_H_state', '_V_state', '_W_state', '_S_state')

@@ -90,7 +90,6 @@ def main():
 def domain_golden():
     """Domain3D of the reference (entities/domain3D.py) on seeded arrays: the assign_* path of the FD examples
     (Tests/FD/Fenton_sphere/fenton.py:86-101) and the anisotropic conductivity / fibre-dyadic conventions."""
-    import types
     # the reference's Domain3D imports its ImageData reader (imageio / nibabel): not needed on the assign path
     from gpuSolve.entities.domain3D import Domain3D
     rng = np.random.default_rng(11)

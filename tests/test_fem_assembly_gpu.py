@@ -4,7 +4,6 @@ included), values within 2e-6 of the largest entry (the reference accumulates fp
 sums rounded once).  Edges, Trias with two regions + fibres (anisotropic tensors), Tetras, with and without RCM."""
 import numpy as np
 import pytest
-import torch
 
 from oracle import fem as ofem
 
