@@ -13,7 +13,10 @@ decomposed along the slowest axis with one-plane NCCL halo exchange per time ste
 Printed JSON (rank 0): value = whole-job node-steps/s with state resident in HBM; e2e = same
 metric with the potential uploaded from pinned host memory before and read back after every
 frame; roofline = algorithmic bytes (32 B per node-step) / kernel time vs the measured HBM
-peak; cpu_baseline = the reference path's op-for-op restatement timed on this box's cores.
+peak; cpu_baseline = the reference path's op-for-op restatement timed on this box's cores;
+other_configs (N=1 only, after the contract measurement, child processes, --skip-extras to omit) = records of
+BASELINE.json's other single-GPU configurations from the tools/ scripts (config 2, config 5 on one GPU, config 1,
+large-system semi-implicit step) - they are not the metric.
 """
 import argparse
 import json
@@ -275,10 +278,45 @@ def run_ours(args):
         }
         if world == 1 and not args.skip_cpu:
             out['cpu_baseline'] = cpu_baseline(sample_n=256, nsteps=3)
+        if world == 1 and not args.skip_extras:
+            try:
+                del st, fd
+                torch.cuda.empty_cache()
+                out['other_configs'] = other_configs()
+            except Exception as e:          # records only: never let them break the contract line
+                out['other_configs'] = [{'error': repr(e)[:200]}]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+# ------------------------------------------------------------------------------ other configs
+def other_configs():
+    """Throughput of BASELINE.json's other single-GPU configurations, measured by the tools/ scripts in child
+    processes AFTER the contract measurement (they are records, not the metric): config 2 (2-D 1024^2, per-step graph
+    vs SM-resident kernel), config 5 on one GPU (2e7-node tetrahedral mesh, SELL-32 explicit lumped step), config 1
+    (63 001-node semi-implicit example) and the large-system semi-implicit step (partitioned PCG, world = 1).
+    A failing or slow child only leaves its entry out."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    runs = [('tools/bench_config2.py', ['--steps', '1000'], 90), ('tools/bench_fem.py', [], 150),
+            ('tools/bench_fem_semi.py', ['--size', '160'], 90)]
+    got = []
+    for script, extra, limit in runs:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(here, script)] + extra, capture_output=True, text=True,
+                               timeout=limit, cwd=here)
+            for line in r.stdout.splitlines():
+                if line.startswith('{'):
+                    d = json.loads(line)
+                    d['tool'] = script
+                    got.append(d)
+            if r.returncode != 0:
+                got.append({'tool': script, 'error': (r.stderr or '').strip().splitlines()[-1:] or ['exit %d' % r.returncode]})
+        except Exception as e:      # timeout, missing file, bad JSON: a record less, never a failed bench
+            got.append({'tool': script, 'error': repr(e)[:200]})
+    return got
 
 
 # ------------------------------------------------------------------------------ CPU baseline
@@ -339,6 +377,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--skip-cpu', action='store_true', help='omit the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--skip-extras', action='store_true', help='omit the other_configs records (tools/ child processes)')
     args = ap.parse_args()
     out = run_reference(args) if args.impl == 'reference' else run_ours(args)
     if out is not None:
