@@ -271,6 +271,7 @@ def run_ours(args):
                     'what': e2e_what},
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'frac_of_nominal_8000_gbs': achieved / 8000.0,
                          'traffic': tr.get('dram_bytes_per_launch') if tr else None,
                          'kernel': 'fd_tma_kernel<FENTON4V,homog,FAST,3D,TMA-staged states>', 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': nodes_local * BYTES_PER_NODE_STEP,
