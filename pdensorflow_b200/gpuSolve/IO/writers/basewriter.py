@@ -34,7 +34,8 @@ class BaseWriter:
         self._fname = 'out'
         self._every_N = None
         self._max_chunk_mb = 500
-        self._chunk_files = []
+        self._buffer = []             # frames of the current (un-flushed) chunk: views into the pinned chunk buffer
+        self._bw_chunk_files = []
         self._counter = 0
         self._chunk_index = 0
         self._chunk_bytes = 0
@@ -60,6 +61,18 @@ class BaseWriter:
         self._bw_last_copy = None
         self._bw_open_chunk = False   # part of the current chunk has already gone to the writer thread
         self._bw_pieces = 0           # pinned buffers handed to the writer thread so far
+
+    # temporary chunk files written so far.  Reading it waits for the background writer, so that - as with the
+    # reference's synchronous flush (basewriter.py:77-93) - every chunk flushed so far is on disk when it is looked at.
+    @property
+    def _chunk_files(self):
+        if self._bw_queue is not None:
+            self._bw_queue.join()
+        return self._bw_chunk_files
+
+    @_chunk_files.setter
+    def _chunk_files(self, value):
+        self._bw_chunk_files = value
 
     # ---- reference API --------------------------------------------------------------------------
     def set_fname(self, fname):
@@ -97,6 +110,7 @@ class BaseWriter:
         else:
             slot.copy_(torch.from_numpy(np.ascontiguousarray(data, dtype=_np_dtype(self._bw_dtype))))
         self._bw_fill += 1
+        self._buffer.append(slot)
         self._counter += 1
         self._chunk_bytes += self._estimate_frame_bytes(slot)
         logical = self._should_flush()
@@ -113,7 +127,7 @@ class BaseWriter:
         """Flush, wait for the background writes, aggregate the chunks into the final file."""
         self.flush_chunk()
         self._bw_drain()
-        self._aggregate(self._chunk_files)
+        self._aggregate(self._bw_chunk_files)
         self._cleanup_chunks()
 
     def wait(self):
@@ -169,10 +183,10 @@ class BaseWriter:
         return fname if fname.endswith('.npy') else '{0}.npy'.format(fname)
 
     def _cleanup_chunks(self):
-        for f in self._chunk_files:
+        for f in self._bw_chunk_files:
             if f is not None and os.path.exists(f):
                 os.remove(f)
-        self._chunk_files = []
+        self._bw_chunk_files = []
 
     # ---- pipeline -------------------------------------------------------------------------------
     def _bw_setup(self, shape, dtype):
@@ -228,6 +242,7 @@ class BaseWriter:
         if close_chunk:
             self._chunk_index += 1
             self._chunk_bytes = 0
+            self._buffer = []
 
     def _bw_worker(self):
         while True:
@@ -241,8 +256,8 @@ class BaseWriter:
                     if ev is not None:
                         ev.synchronize()
                     path = self._write_chunk(self._bw_host[buf][:n].numpy(), idx)
-                    if path is not None and path not in self._chunk_files:
-                        self._chunk_files.append(path)
+                    if path is not None and path not in self._bw_chunk_files:
+                        self._bw_chunk_files.append(path)
             except BaseException as e:      # reported on the caller's thread
                 self._bw_error = e
             finally:

@@ -178,3 +178,53 @@ def test_domain3d_voxel_files(tmp_path):
     assert np.array_equal(T[..., 1], fib[..., 0] * fib[..., 1]) and np.array_equal(T[..., 5], fib[..., 2] ** 2)
     with pytest.raises(NotImplementedError):
         Domain3D().load_geometry_file('atria.png', 10, 10)
+
+
+def test_reference_basewriter_unit_tests(tmp_path):
+    """Tests/CICD/unit/test_basewriter.py:49-148 transcribed (NumPy frames instead of TF tensors): a chunk is flushed
+    exactly on multiples of every_N / as soon as max_chunk_mb is exceeded, un-flushed frames are held in `_buffer`,
+    every flushed chunk is a file on disk when `_chunk_files` is looked at, the aggregate equals the input."""
+    from pdensorflow_b200.gpuSolve.IO.writers import BaseWriter
+    n, N, nx = 10, 3, 128
+    fname = str(tmp_path / 'every_n')
+    writer = BaseWriter({'fname': fname, 'every_N': N})
+    rng = np.random.default_rng(0)
+    frames = [rng.uniform(size=(nx,)).astype(np.float32) for _ in range(n)]
+    ref = np.stack(frames, axis=0)
+    prev = 0
+    for i, frame in enumerate(frames, start=1):
+        writer.add_solution(frame)
+        expected = i // N
+        assert writer.nb_chunks() == (prev + 1 if i % N == 0 else prev)
+        prev = writer.nb_chunks()
+        assert len(writer._buffer) == i - expected * N
+        assert len(writer._chunk_files) == expected
+        for cf in writer._chunk_files:
+            assert os.path.exists(cf)
+    assert len(writer._buffer) == n % N
+    writer.finalize()
+    out = np.load(fname + '.npy')
+    assert out.shape == (n, nx)
+    np.testing.assert_allclose(out, ref, rtol=1e-6, atol=1e-6)
+    assert writer._chunk_files == []
+    # memory trigger: 0.76 MB frames against a 1 MB threshold -> a dump every second frame
+    nelem = 200000
+    fname = str(tmp_path / 'max_mb')
+    writer = BaseWriter({'fname': fname, 'max_chunk_mb': 1})
+    assert writer._every_N is None
+    frames = [np.ones((nelem,), dtype=np.float32) * float(k) for k in range(5)]
+    writer.add_solution(frames[0])
+    assert writer.nb_chunks() == 0
+    writer.add_solution(frames[1])
+    assert writer.nb_chunks() == 1 and len(writer._chunk_files) == 1 and os.path.exists(writer._chunk_files[0])
+    assert len(writer._buffer) == 0
+    writer.add_solution(frames[2])
+    assert writer.nb_chunks() == 1
+    writer.add_solution(frames[3])
+    assert writer.nb_chunks() == 2
+    writer.add_solution(frames[4])
+    assert writer.nb_chunks() == 2
+    writer.finalize()
+    out = np.load(fname + '.npy')
+    assert out.shape == (len(frames), nelem)
+    np.testing.assert_allclose(out, np.stack(frames), rtol=1e-6, atol=1e-6)
