@@ -110,3 +110,71 @@ def test_pcg_recovers_gold_solution():
         assert nit < 1000
         assert np.linalg.norm(x - gold) / np.linalg.norm(gold) < 1e-3
         assert np.linalg.norm(b - fem.spmv(A['rowptr'], A['col'], val, x)) / np.linalg.norm(b) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's own end-to-end acceptance tests of MonodomainSolver + assembly + PCG + mMS, run on the ORACLE:
+# Tests/CICD/unit/test_mms_1d.py:44-176 (cable) and Tests/CICD/nightly/test_mms_2d_regression.py:50-184 (sheet;
+# its bundled mesh is missing from the checkout, the synthetic triangulated square has the same 0.04 spacing).
+# ------------------------------------------------------------------------------------------------
+def _lat(Vrec, times, vth):
+    lat = np.full(Vrec.shape[1], np.nan)
+    for j in range(Vrec.shape[1]):
+        v = Vrec[:, j]
+        k = int(np.argmax((v[:-1] < vth) & (v[1:] >= vth)))
+        if (v[k] < vth) and (v[k + 1] >= vth):
+            lat[j] = times[k] + (vth - v[k]) / (v[k + 1] - v[k]) * (times[k + 1] - times[k])
+    return lat
+
+
+def _mms_front(Pts, elems, fibres, sigma, dt, tend, xfrac, rcm):
+    from oracle import ionic as oi
+    ionic = oi.ModifiedMS2v(dt=dt)
+    sig = {r: sigma for r in (1, 2, 3, 4)}
+    orc = fem.MonodomainOracle(ionic, Pts, elems, fibres, sig, sig, dt, use_renumbering=rcm, maxiter=Pts.shape[0] // 2)
+    x = Pts[:, 0].copy()
+    U0 = np.where(x < xfrac * x.max(), 20.0, -80.0).astype(np.float32)
+    orc.U = U0[:, None].copy()
+    ionic.initialize_state_variables(orc.U)
+    orc.finalize_for_run()
+    nt = int(tend // dt)
+    Vrec = np.empty((nt + 1, x.shape[0]), dtype=np.float32)
+    times = np.zeros(nt + 1)
+    Vrec[0] = orc.U_user().ravel()
+    t = 0.0
+    for i in range(nt):
+        t += dt
+        orc.step(t)
+        Vrec[i + 1] = orc.U_user().ravel()
+        times[i + 1] = t
+    lat = _lat(Vrec, times, -30.0)
+    Lx = x.max()
+    mask = (x >= 0.4 * Lx) & (x <= 0.8 * Lx) & np.isfinite(lat)
+    cv = 1.0 / float(np.polyfit(x[mask], lat[mask], 1)[0])
+    u_crit, tau_in = float(ionic.get_parameter('u_crit')), float(ionic.get_parameter('tau_in'))
+    return x, lat, Vrec, cv, 0.5 * (1.0 - 2.0 * u_crit) * np.sqrt(2.0 * sigma / tau_in)
+
+
+def test_reference_mms_1d_acceptance_on_the_oracle():
+    from pdensorflow_b200.gpuSolve.entities.synthetic import cable
+    P, E, F = cable(150, 2.0)
+    x, lat, Vrec, cv, cv_an = _mms_front(P, E, F, 0.1, 0.05, 7.0, 0.05, False)
+    interior = (x >= 0.4 * 2.0) & (x <= 0.8 * 2.0)
+    assert np.all(np.isfinite(Vrec)) and np.all(np.isfinite(lat[interior])) and np.all(np.diff(lat[interior]) > 0.0)
+    assert Vrec.min() > -81.0 and Vrec.max() < 21.0
+    assert abs(cv - cv_an) / cv_an < 0.10, (cv, cv_an)
+
+
+def test_reference_mms_2d_regression_on_the_oracle():
+    from pdensorflow_b200.gpuSolve.entities.synthetic import triangulated_square
+    P, E, F = triangulated_square(126, 126, 5.0, 5.0)          # 0.04 spacing as the reference's sheet, a quarter of its area
+    x, lat, Vrec, cv, cv_an = _mms_front(P, E, F, 0.5, 0.05, 5.0, 0.05, True)
+    Lx = x.max()
+    assert np.all(np.isfinite(Vrec))
+    xr = np.round(x, 6)
+    xu = np.sort(np.unique(xr))
+    xu = xu[(xu >= 0.4 * Lx) & (xu <= 0.8 * Lx)]
+    col = np.array([np.nanmean(lat[xr == v]) for v in xu])
+    assert np.all(np.isfinite(col)) and np.all(np.diff(col) > 0.0)
+    assert Vrec.min() > -81.0 and Vrec.max() < 21.0
+    assert abs(cv - cv_an) / cv_an < 0.10, (cv, cv_an)
