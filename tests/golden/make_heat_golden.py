@@ -79,6 +79,50 @@ def main():
         out[tag + '_geometry'] = np.asarray(model.domain(), dtype=np.float32)
         out[tag + '_V'] = model._V_state.numpy()
         print(tag, len(cap.frames), cap.frames[-1].min(), cap.frames[-1].max(), out[tag + '_geometry'].mean())
+    # ---- Tests/FEM/HeatEquation/heat.py: HeatSolver.step (implicit Euler heat equation, two stimuli through the float-time
+    # interface, RCM renumbering) on a small perturbed square, the example's own dfmass / sigmaTens callbacks -----------
+    import pickle
+    import tempfile
+    from make_ref_golden import square_mesh
+    from gpuSolve.physics import HeatSolver
+    hx = load_example('Tests/FEM/HeatEquation/heat.py', 'ref_fem_heat_example')
+    mesh = square_mesh(12, 2.0, seed=3)
+    fn = os.path.join(tempfile.mkdtemp(), 'sq.pkl')
+    with open(fn, 'wb') as f:
+        pickle.dump(mesh, f)
+    dt = 0.1
+    model = HeatSolver({'mesh_file_name': fn, 'use_renumbering': True, 'dt': dt, 'dt_per_plot': 1, 'Tend': 20.0})
+    regions = np.unique(mesh['Elems']['Trias'][:, -1])
+    model.add_element_material_property('sigma_l', 'region', {int(r): 0.02 for r in regions})
+    model.add_element_material_property('sigma_t', 'region', {int(r): 0.005 for r in regions})
+    model.add_material_function('mass', hx.dfmass)
+    model.add_material_function('stiffness', hx.sigmaTens)
+    model.assemble_matrices()
+    pts = mesh['Pts']
+    Lx, Ly = pts[:, 0].max(), pts[:, 1].max()
+    model.set_initial_condition()
+    s1 = (pts[:, 0] < 0.2 * Lx).astype(np.float32).reshape(-1, 1)
+    s2 = np.logical_and(pts[:, 0] < 0.6 * Lx, pts[:, 1] < 0.5 * Ly).astype(np.float32).reshape(-1, 1)
+    p1 = {'tstart': 0.0, 'nstim': 1, 'period': 200, 'duration': 0.4, 'intensity': 5.0, 'name': 'S1'}
+    p2 = {'tstart': 1.5, 'nstim': 3, 'period': 1.0, 'duration': 0.4, 'intensity': 5.0, 'name': 'crossstim'}
+    model.add_stimulus(s1, p1)
+    model.add_stimulus(s2, p2)
+    model.solver().set_maxiter(pts.shape[0] // 2)
+    model.finalize_for_run()
+    frames, iters, ctime = [np.array(model.U())], [], 0.0
+    for i in range(50):
+        ctime += model.dt()
+        model.step(ctime)
+        iters.append(int(model.solver()._niters))
+        if (i + 1) % 5 == 0:
+            frames.append(np.array(model.U()))
+    out['femheat_pts'], out['femheat_Trias'], out['femheat_fibres'] = pts, mesh['Elems']['Trias'], mesh['Fibres']
+    out['femheat_frames'] = np.stack(frames)[:, :, 0]
+    out['femheat_iters'] = np.array(iters)
+    out['femheat_s1'], out['femheat_s2'] = s1, s2
+    out['femheat_p1'] = np.array([p1[k] for k in ('tstart', 'nstim', 'period', 'duration', 'intensity')], dtype=np.float64)
+    out['femheat_p2'] = np.array([p2[k] for k in ('tstart', 'nstim', 'period', 'duration', 'intensity')], dtype=np.float64)
+    print('femheat:', pts.shape[0], 'nodes, CG iterations', min(iters), '..', max(iters), 'U range', frames[-1].min(), frames[-1].max())
     np.savez_compressed(os.path.join(HERE, 'ref_heat.npz'), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -375,6 +375,33 @@ def test_monodomain_solver_vs_reference_source(tag, ionic, etype, stim):
     assert err < 1e-6, err
 
 
+def test_heat_solver_vs_reference_source():
+    """Tests/FEM/HeatEquation/heat.py: HeatSolver.step (implicit Euler heat equation; anisotropic tensors from the example's
+    own sigmaTens callback, sigma_l = 0.02 / sigma_t = 0.005 along x; RCM; two stimuli through the float-time interface, the
+    second one with three pulses) run by the reference's own source: same CG iteration counts, potentials to PCG tolerance."""
+    g = gold('ref_heat.npz')
+    pts, elems = g['femheat_pts'], {'Trias': g['femheat_Trias']}
+    regions = np.unique(elems['Trias'][:, -1])
+    mo = ofem.MonodomainOracle(None, pts, elems, g['femheat_fibres'], {int(r): 0.02 for r in regions},
+                               {int(r): 0.005 for r in regions}, 0.1, use_renumbering=True, maxiter=pts.shape[0] // 2)
+    for mask, p in ((g['femheat_s1'], g['femheat_p1']), (g['femheat_s2'], g['femheat_p2'])):
+        mo.add_stimulus(mask, {'tstart': float(p[0]), 'nstim': int(p[1]), 'period': float(p[2]), 'duration': float(p[3]),
+                               'intensity': float(p[4])})
+    mo.finalize_for_run()
+    frames = [mo.U_user()[:, 0].copy()]
+    ctime = 0.0
+    for i in range(50):
+        ctime += 0.1
+        mo.step(ctime)
+        if (i + 1) % 5 == 0:
+            frames.append(mo.U_user()[:, 0].copy())
+    ref = g['femheat_frames']
+    assert list(mo.niters) == list(g['femheat_iters'])
+    assert ref.max() > 5.0
+    err = np.linalg.norm(np.stack(frames).astype(np.float64) - ref) / np.linalg.norm(ref.astype(np.float64))
+    assert err < 1e-6, err
+
+
 # ------------------------------------------------------------------------------ product host code
 PROD_CRN_V = ['m_A', 'm_B', 'h_A', 'h_B', 'j_A', 'j_B', 'oa_A', 'oa_B', 'oi_A', 'oi_B', 'ua_A', 'ua_B', 'ui_A', 'ui_B',
               'xr_A', 'xr_B', 'xs_A', 'xs_B', 'd_A', 'd_B', 'f_A', 'f_B', 'w_A', 'w_B', 'GKur', 'INaK', 'IbNa', 'ICaL_v',
