@@ -102,3 +102,15 @@ def test_dropin_alias_registers_gpusolve():
             "from gpuSolve.matrices import csr_axpby, localMass; assert Fenton4v().tau_vp() is not None; print('ok')")
     r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0 and 'ok' in r.stdout, r.stderr
+
+
+def test_package_imports_and_reports_version():
+    """Tests/CICD/unit/test_import.py: the package imports (through the drop-in alias) and version() is a dotted numeric
+    string; the IO / entities sub-packages the examples import resolve too."""
+    code = ("import pdensorflow_b200.dropin, gpuSolve; v = gpuSolve.version(); parts = v.split('.'); "
+            "assert isinstance(v, str) and len(parts) >= 2 and all(p.isdigit() for p in parts), v; "
+            "import gpuSolve.IO.writers as w, gpuSolve.IO.readers as r, gpuSolve.entities as e; "
+            "assert w.IGBWriter and w.ResultWriter and w.BaseWriter and r.IGBReader and e.Domain3D and e.Triangulation; "
+            "print('ok')")
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr
