@@ -91,6 +91,10 @@ def test_sass_has_tma_and_no_legacy_tensor_path():
         pytest.skip('cuobjdump unavailable')
     assert 'UTMALDG' in sass and 'SYNCS' in sass
     assert 'sm_100a' in subprocess.run(['cuobjdump', '-lelf', so], capture_output=True, text=True).stdout
+    # partitioned PCG: 8-byte (epoch, value) words published / acquired at SYSTEM scope (peer memory over NVLink)
+    assert 'STG.E.64.STRONG.SYS' in sass and 'LDG.E.64.STRONG.SYS' in sass
+    # resident 2-D kernel (two nodes per thread): 64-bit shared-memory words, GPU-scope flag release / acquire
+    assert 'LDS.64' in sass and 'STS.64' in sass and 'STG.E.STRONG.GPU' in sass and 'LDG.E.STRONG.GPU' in sass
 
 
 def test_dropin_alias_registers_gpusolve():
