@@ -301,8 +301,8 @@ def other_configs():
     A failing or slow child only leaves its entry out."""
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
-    runs = [('tools/bench_config2.py', ['--steps', '1000'], 90), ('tools/bench_fem.py', [], 150),
-            ('tools/bench_fem_semi.py', ['--size', '160'], 90)]
+    runs = [('tools/bench_config2.py', ['--steps', '1000'], 60), ('tools/bench_fem.py', [], 110),
+            ('tools/bench_fem_semi.py', ['--size', '160'], 60)]      # typical: 10 + 35 + 15 s
     got = []
     for script, extra, limit in runs:
         try:
