@@ -103,3 +103,41 @@ def test_structured_consistent_mass_matches_assembly():
     assert np.array_equal(ci, m['col'])
     np.testing.assert_allclose(mv, m['mass'], rtol=0, atol=2e-6 * np.abs(m['mass']).max())
     np.testing.assert_allclose(np.add.reduceat(mv.astype(np.float64), rp[:-1]), ml, rtol=1e-5)
+
+
+@pytest.mark.parametrize('row_lo', [0, 7])
+def test_sell32_conversion_is_a_faithful_relayout(row_lo):
+    """csr_to_sell32: slice s holds rows 32s..32s+31 column-major (entry k of lane l at slice_ptr[s] + 32k + l), short
+    rows padded with (col = the row's own index + row_lo, val = 0); y = A x must be unchanged and the padding small."""
+    from pdensorflow_b200.fem_dist import csr_to_sell32
+    rng = np.random.default_rng(2)
+    n, ncols = 150, 400
+    lens = rng.integers(1, 12, size=n)
+    rowptr = np.zeros(n + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum(lens)
+    col = np.concatenate([np.sort(rng.choice(ncols, size=int(k), replace=False)) for k in lens]).astype(np.int32)
+    val = rng.standard_normal(col.shape[0]).astype(np.float32)
+    sp, scol, sval = csr_to_sell32(rowptr, col, val, row_lo)
+    nsl = (n + 31) // 32
+    assert sp.shape[0] == nsl + 1 and sp[0] == 0 and (np.diff(sp) % 32 == 0).all() and sp[-1] == scol.shape[0] == sval.shape[0]
+    x = rng.standard_normal(ncols).astype(np.float64)
+    y = np.zeros(n)
+    seen = 0
+    for s in range(nsl):
+        width = (sp[s + 1] - sp[s]) // 32
+        assert width == lens[32 * s:32 * s + 32].max()
+        for lane in range(32):
+            row = 32 * s + lane
+            idx = sp[s] + np.arange(width) * 32 + lane
+            if row < n:
+                k = lens[row]
+                assert np.array_equal(scol[idx[:k]], col[rowptr[row]:rowptr[row + 1]])          # row order kept
+                assert np.array_equal(sval[idx[:k]], val[rowptr[row]:rowptr[row + 1]])
+                assert (sval[idx[k:]] == 0).all() and (scol[idx[k:]] == row + row_lo).all()     # padding
+                y[row] = (sval[idx].astype(np.float64) * x[scol[idx]]).sum()
+                seen += k
+            else:
+                assert (sval[idx] == 0).all() and (scol[idx] == n - 1 + row_lo).all()
+    rows = np.repeat(np.arange(n), lens)
+    assert seen == col.shape[0]
+    assert np.allclose(y, np.bincount(rows, weights=val.astype(np.float64) * x[col], minlength=n))
