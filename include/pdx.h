@@ -251,6 +251,10 @@ int  pdx_pcg_solve(pdx_pcg* s, const float* b, float* x, int maxiter, double tol
 int  pdx_pcg_solve_rhs0(pdx_pcg* s, const float* mval, const float* rhs0, float* x, int maxiter, double toll,
                         int check_every, int32_t* info /* device, 4 words */, void* stream);
 
+/* Optional: tell the library the size of a CSR matrix once, when it is uploaded (the kernels pick their lanes-per-row
+ * from nnz / n; without the hint pdx_fem_explicit_step uses 8 lanes - it never reads rowptr back). */
+int pdx_csr_hint(const int32_t* rowptr, int32_t n, int64_t nnz);
+
 /* Explicit mass-lumped FEM step named by the north star (no reference implementation;
  * SURVEY.md section 8a row E): U1 = U + dt*(dU + I0) - dt * mlinv * (K U), fused with the
  * ionic update (row-per-warp CSR). */

@@ -99,3 +99,89 @@ def time_fd(shape, nsteps, dt=0.1, diff=0.8, spacing=(1.0, 1.0, 1.0), threads=No
     for _ in range(nsteps):
         U = fd_step(m, U, dt, diff, spacing)
     return time.perf_counter() - t0, threads, U
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 2-D step (config 2) and the FEM steps (configs 1 and 5), same op-for-op style
+def _sympad2(X):
+    return F.pad(X[None, None], (1, 1, 1, 1), mode='replicate')[0, 0]
+
+
+def fd_step_2d(model, U, dt, diff, spacing):
+    """The examples' solve() transcribed to 2-D with gpuSolve/diffop2D/laplace_homogeneous_isotropic_diffusion.py:3-36."""
+    U0 = _sympad2(U[1:-1, 1:-1])
+    X = _sympad2(U0)
+    DX, DY = spacing
+    c = X[1:-1, 1:-1]
+    lap = ((X[0:-2, 1:-1] - 2.0 * c + X[2:, 1:-1]) / (DX * DX) + (X[1:-1, 0:-2] - 2.0 * c + X[1:-1, 2:]) / (DY * DY))
+    return U0 + dt * model.differentiate(U) + (diff * dt) * lap
+
+
+def time_fd_2d(shape, nsteps, dt=0.1, diff=0.8, spacing=(1.0, 1.0), threads=None):
+    import os
+    import time
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    U = torch.full(shape, -80.0, dtype=torch.float32)
+    U[0:2] = 20.0
+    m = Fenton4v(dt)
+    m.initialize_state_variables(U)
+    U = fd_step_2d(m, U, dt, diff, spacing)
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        U = fd_step_2d(m, U, dt, diff, spacing)
+    return time.perf_counter() - t0, threads, U
+
+
+def pcg(A, minv, b, x0, maxiter, toll=1e-5, check_every=5):
+    """gpuSolve/linearsolvers/conjgrad.py:172-203,287-301 (eager path) on torch-CPU: one op per line, a host
+    read of the residual every ``check_every`` iterations like the reference's ``.numpy()``."""
+    x = x0
+    r = b - A @ x
+    z = minv * r
+    p = z
+    rz = torch.sum(r * z)
+    toll_sq = toll * toll
+    n = 0
+    for n in range(1, 1 + maxiter):
+        q = A @ p
+        alpha = rz / torch.sum(p * q)
+        x = x + alpha * p
+        r = r - alpha * q
+        res = torch.sum(r * r)
+        z = minv * r
+        rznew = torch.sum(r * z)
+        beta = rznew / rz
+        p = z + beta * p
+        if n % check_every == 0:
+            rv = float(res)
+            if rv != rv or rv in (float('inf'), float('-inf')) or rv < toll_sq:
+                break
+        rz = rznew
+    return x, n
+
+
+def semi_implicit_step(model, U, I0, dt, MASS, A, minv, maxiter):
+    """MonodomainSolver.solve_step (gpuSolve/physics/monodomainSolver.py:98-108): ionic update, RHS = MASS (U + dt (dU
+    + I0)), Jacobi-PCG solve of (MASS + dt STIFFNESS) U1 = RHS from the guess U.  MASS / A are torch sparse CSR."""
+    dU = model.differentiate(U) + I0
+    rhs = MASS @ (U + dt * dU)
+    return pcg(A, minv, rhs, U, maxiter)
+
+
+def explicit_lumped_step(model, U, I0, dt, K, mlinv):
+    """Row E (no reference implementation): U1 = U + dt (dU + I0) - dt M_L^-1 (K U), unfused, torch sparse CSR."""
+    dU = model.differentiate(U) + I0
+    return U + dt * dU - dt * (mlinv * (K @ U))
+
+
+def sparse_csr(rowptr, col, val, n):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')          # "sparse CSR support is in beta"
+        return _sparse_csr(rowptr, col, val, n)
+
+
+def _sparse_csr(rowptr, col, val, n):
+    return torch.sparse_csr_tensor(torch.as_tensor(rowptr, dtype=torch.int64), torch.as_tensor(col, dtype=torch.int64),
+                                   torch.as_tensor(val, dtype=torch.float32), size=(n, n))

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <utility>
 #include <unordered_map>
@@ -15,6 +16,26 @@ static std::atomic<int64_t> g_launches{0};
 
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int sm_count() {
+    static std::atomic<int> cached[PDX_MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PDX_MAX_DEVICES) return 148;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+static std::mutex g_hint_mu;
+static std::unordered_map<const void*, int> g_hint;
+int csr_group_hint(const int32_t* rowptr) {
+    std::lock_guard<std::mutex> lk(g_hint_mu);
+    auto it = g_hint.find(rowptr);
+    return it == g_hint.end() ? 0 : it->second;
+}
+
 int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return 0;
     set_error(std::string(what) + ": " + cudaGetErrorString(e));
@@ -142,6 +163,16 @@ extern "C" {
 int pdx_version(void) { return PDX_VERSION; }
 const char* pdx_last_error(void) { return g_err.c_str(); }
 int64_t pdx_launch_count(void) { return g_launches.load(); }
+
+int pdx_csr_hint(const int32_t* rowptr, int32_t n, int64_t nnz) {
+    if (!rowptr || n <= 0 || nnz < 0) { set_error("pdx_csr_hint: bad arguments"); return 1; }
+    const double mean = (double)nnz / n;
+    const int G = mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 24 ? 16 : 32;
+    std::lock_guard<std::mutex> lk(g_hint_mu);
+    if (g_hint.size() > 256) g_hint.clear();
+    g_hint[rowptr] = G;
+    return 0;
+}
 
 int pdx_model_num_params(int model) {
     switch (model) {
@@ -316,6 +347,10 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     p->base.nty = (d.ny + ty - 1) / ty;
     p->base.ntz = (d.nz + tz - 1) / tz;
     p->base.x_chunk = d.x_chunk > 0 ? d.x_chunk : fd_tma_auto_chunk(d);
+    {   // CTA rasterisation of the TMA kernel (pdx_fd_tma.cu): 1 = x-chunks fastest, alternating march direction
+        const char* e = std::getenv("PDX_FD_RASTER");           // A/B switch
+        p->base.raster = (e && e[0] == '0') ? 0 : 1;
+    }
     if (kernel == PDX_KERNEL_TMA) {
         // set the kernel's shared-memory attribute now (an empty range launches nothing), so
         // that the first real step can already be inside a CUDA-graph capture

@@ -155,7 +155,7 @@ template <int MODEL>
 int launch_ionic_model(int math, bool nodal, const IonicArgs& a, cudaStream_t s) {
     const int block = 256;
     int64_t nb = (a.n + block - 1) / block;
-    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb > sm_count() * 16) nb = sm_count() * 16;
     if (nb < 1) nb = 1;
     if (nodal) ionic_kernel<MODEL, PDX_MATH_EXACT, true><<<(unsigned)nb, block, 0, s>>>(a);
     else if (math == PDX_MATH_EXACT) ionic_kernel<MODEL, PDX_MATH_EXACT, false><<<(unsigned)nb, block, 0, s>>>(a);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) stim_max_kernel(float* U, const float* ma
 
 int launch_stim_max(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s) {
     int64_t nb = (n + 255) / 256;
-    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb > sm_count() * 16) nb = sm_count() * 16;
     if (nb < 1) nb = 1;
     stim_max_kernel<<<(unsigned)nb, 256, 0, s>>>(U, mask, intensity, n);
     count_launch();
@@ -212,7 +212,7 @@ int launch_stim_max(float* U, const float* mask, float intensity, int64_t n, cud
 
 int launch_stim(float* U, const float* mask, float intensity, int64_t n, cudaStream_t s) {
     int64_t nb = (n + 255) / 256;
-    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb > sm_count() * 16) nb = sm_count() * 16;
     if (nb < 1) nb = 1;
     stim_kernel<<<(unsigned)nb, 256, 0, s>>>(U, mask, intensity, n);
     count_launch();

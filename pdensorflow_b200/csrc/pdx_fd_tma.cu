@@ -120,20 +120,31 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
     unsigned char* sring = smem + NSTAGE * G::SLOT_BYTES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int b = blockIdx.x;
+    // Rasterisation.  raster 0: tiles fastest, x-chunks slowest (an x-layer of CTAs at a time).
+    // raster 1 (3-D): x-chunks fastest, and odd chunks march DOWNWARDS: the resident set then holds every
+    // chunk of a few tiles, neighbouring chunks start together at their shared planes (c even: planes
+    // 8c+7, 8c+8) and meet again at the other pair when they finish, so the two halo planes a chunk
+    // re-reads are in L2 whatever the plane size (a 2048^2 layer of CTAs is 9 waves: its halo planes
+    // are long evicted when the next layer runs).
+    int b = blockIdx.x, chunk;
+    if (HAS_X && a.raster) { chunk = b % a.nchunk; b /= a.nchunk; }
     const int tz = b % a.ntz;  b /= a.ntz;
     const int ty = b % a.nty;  b /= a.nty;
+    if (!(HAS_X && a.raster)) chunk = b;
     const int z0 = tz * TZ, y0 = ty * TY;
-    const int xb = a.xb + b * a.x_chunk;
+    const int xb = a.xb + chunk * a.x_chunk;
     const int xe = min(xb + a.x_chunk, a.xe);
     const int np = xe - xb;
     const int nlog = HAS_X ? np + 2 : np;           // logical planes q = xb-1 .. xe (3-D)
-    const int q0 = HAS_X ? xb - 1 : xb;
+    const bool down = HAS_X && a.raster && (chunk & 1);   // CTA uniform
+    const int qs = down ? -1 : 1;                   // logical plane j is array plane q0 + qs*j
+    const int q0 = HAS_X ? (down ? xe : xb - 1) : xb;
+    const int p0 = down ? xe - 1 : xb;              // i-th plane advanced: p0 + qs*i
 
     auto slotU = [&](int j) { return reinterpret_cast<float*>(smem + (j % NSTAGE) * G::SLOT_BYTES); };
     auto slotD = [&](int j) { return reinterpret_cast<float*>(smem + (j % NSTAGE) * G::SLOT_BYTES + G::FIELD_BYTES); };
     auto issue = [&](int j) {   // thread 0 only
-        const int q = q0 + j;
+        const int q = q0 + qs * j;
         uint64_t* bar = &full[j % NSTAGE];
         mbar_expect_tx(bar, G::TX_BYTES);
         tma_load_3d(slotU(j), &mapU, z0 - ZH, y0 - 1, HAS_X ? clampi(q, a.xclo, a.xchi) : q, bar);
@@ -147,7 +158,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
         uint64_t* bar = &sfull[i % SSTAGES];
         mbar_expect_tx(bar, NS * G::ST_BYTES);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) tma_load_3d(sslot(i, s), &mapS.m[s], z0, y0, xb + i, bar);
+        for (int s = 0; s < NS; ++s) tma_load_3d(sslot(i, s), &mapS.m[s], z0, y0, p0 + qs * i, bar);
     };
 
     if (tid == 0) {
@@ -202,13 +213,13 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             for (int s = 0; s < NS; ++s) stn[r][s] = ldg4(a.st[s] + gi);
         }
     };
-    if (!TST && NS > 0 && np > 0) load_states(xb);
+    if (!TST && NS > 0 && np > 0) load_states(p0);
     int srow[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) srow[r] = (warp * R + r) * TZ + 4 * lane;
 
     for (int i = 0; i < np; ++i) {
-        const int p = xb + i;
+        const int p = p0 + qs * i;
         const int jc = HAS_X ? i + 1 : i;
         if (HAS_X) {
             if (i == 0) { wait_plane(0); wait_plane(1); }
@@ -217,8 +228,8 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             wait_plane(i);
         }
         const float* Sc = slotU(jc);
-        const float* Sm = HAS_X ? slotU(jc - 1) : Sc;
-        const float* Sp = HAS_X ? slotU(jc + 1) : Sc;
+        const float* Sm = HAS_X ? slotU(jc - qs) : Sc;      // array plane p - 1
+        const float* Sp = HAS_X ? slotU(jc + qs) : Sc;      // array plane p + 1
         const bool raw_diff = yb_tile || zb_tile || (HAS_X && (p < a.xclo || p > a.xchi));   // CTA uniform
 
         F4 stc[R][NS > 0 ? NS : 1];
@@ -235,7 +246,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int s = 0; s < NS; ++s) stc[r][s] = stn[r][s];
-            if (NS > 0 && i + 1 < np) load_states(p + 1);
+            if (NS > 0 && i + 1 < np) load_states(p + qs);
         }
 
 #pragma unroll
@@ -266,7 +277,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
                 dzl = dlo1 ? dc.v[0] : Dc[drc - 1];
                 dzr = dhi1 ? dc.v[3] : Dc[drc + 4];
                 dym = lds4(Dc + drm[r]); dyp = lds4(Dc + drp[r]);
-                if (HAS_X) { dxm = lds4(slotD(jc - 1) + drc); dxp = lds4(slotD(jc + 1) + drc); }
+                if (HAS_X) { dxm = lds4(slotD(jc - qs) + drc); dxp = lds4(slotD(jc + qs) + drc); }
             }
             F4 out;
 #pragma unroll
@@ -318,20 +329,26 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
 }
 
 template <int MODEL, bool HET, int MATH, bool HAS_X, int R, bool TST>
-int launch_inst(const FdArgs& a, const CUtensorMap& mU, const CUtensorMap& mD, const StateMaps& mS, cudaStream_t s) {
+int launch_inst(const FdArgs& a0, const CUtensorMap& mU, const CUtensorMap& mD, const StateMaps& mS, cudaStream_t s) {
     using G = Geo<R, HET, TST ? NStates<MODEL>::value : 0>;
     auto kern = fd_tma_kernel<MODEL, HET, MATH, HAS_X, R, TST>;
-    static bool attr_done = false;   // per instantiation
-    if (!attr_done) {
+    // the opt-in to > 48 KB of dynamic shared memory is a PER-DEVICE function attribute: one flag per
+    // instantiation and device ordinal (a process may drive several GPUs)
+    static bool attr_done[PDX_MAX_DEVICES] = {};
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+    if (dev < 0 || dev >= PDX_MAX_DEVICES || !attr_done[dev]) {
         if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES),
                        "cudaFuncSetAttribute(smem)"))
             return 1;
-        attr_done = true;
+        if (dev >= 0 && dev < PDX_MAX_DEVICES) attr_done[dev] = true;
     }
-    const int nplanes = a.xe - a.xb;
+    const int nplanes = a0.xe - a0.xb;
     if (nplanes <= 0) return 0;
-    const int nchunk = (nplanes + a.x_chunk - 1) / a.x_chunk;
-    const long long nb = (long long)a.ntz * a.nty * nchunk;
+    FdArgs a = a0;
+    a.nchunk = (nplanes + a.x_chunk - 1) / a.x_chunk;
+    if (!HAS_X || a.nchunk < 2) a.raster = 0;
+    const long long nb = (long long)a.ntz * a.nty * a.nchunk;
     if (nb > 0x7fffffffLL) { set_error("fd_tma: grid too large"); return 1; }
     kern<<<(unsigned)nb, NTHREADS, G::SMEM_BYTES, s>>>(mU, mD, mS, a);
     count_launch();

@@ -294,7 +294,7 @@ int pdx_csr_spmv(int32_t n, const int32_t* rowptr, const int32_t* col, const flo
     constexpr int G = 8;
     long long threads = (long long)n * G;
     long long nb = (threads + 255) / 256;
-    if (nb > 148LL * 32) nb = 148LL * 32;
+    if (nb > (long long)sm_count() * 32) nb = (long long)sm_count() * 32;
     // round rows per pass so that groups stay converged: handled by the kernel loop bound (row < n)
     spmv_kernel<G><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(n, rowptr, col, val, x, y);
     count_launch();
@@ -425,21 +425,12 @@ static int explicit_step_impl(bool sell, int model, int math_mode, const float* 
         return 1;
     }
     // lanes per row from the mean row length (P1 triangles ~7, tetrahedra ~15 entries per row)
-    int G = 8;
-    {
-        static thread_local const int32_t* cached_rp = nullptr;
-        static thread_local int cached_G = 8;
-        if (cached_rp != rowptr) {
-            int32_t last = 0;
-            if (cudaMemcpy(&last, rowptr + n, sizeof(int32_t), cudaMemcpyDeviceToHost) == cudaSuccess) {
-                cached_G = pick_group(n, last);
-                cached_rp = rowptr;
-            }
-        }
-        G = cached_G;
-    }
+    // (registered once per matrix through pdx_csr_hint; 8 lanes when the caller gave no hint - no device read here,
+    // so the call never blocks and is safe inside a stream capture)
+    int G = csr_group_hint(rowptr);
+    if (G == 0) G = 8;
     long long nb = ((long long)n * G + 255) / 256;
-    if (nb > 148LL * 32) nb = 148LL * 32;
+    if (nb > (long long)sm_count() * 32) nb = (long long)sm_count() * 32;
     switch (model) {
         case PDX_MODEL_NONE:     return launch_expl<PDX_MODEL_NONE, PDX_MATH_FAST>(G, a, (unsigned)nb, s);
         case PDX_MODEL_FENTON4V: return ex ? launch_expl<PDX_MODEL_FENTON4V, PDX_MATH_EXACT>(G, a, (unsigned)nb, s)

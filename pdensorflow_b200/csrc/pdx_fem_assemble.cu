@@ -153,7 +153,7 @@ int pdx_fem_assemble(int nv, int64_t ne, const int32_t* elems, int elem_stride, 
     if (ne == 0) return 0;
     AsmArgs a{ne, elems, elem_stride, pts, rowid, sigma, rowptr, col, mass_acc, stiff_acc, status};
     int64_t nb = (ne + 127) / 128;
-    if (nb > 148LL * 64) nb = 148LL * 64;
+    if (nb > (long long)sm_count() * 64) nb = (long long)sm_count() * 64;
     cudaStream_t s = (cudaStream_t)stream;
     if (nv == 2) fem_assemble_kernel<2><<<(unsigned)nb, 128, 0, s>>>(a);
     else if (nv == 3) fem_assemble_kernel<3><<<(unsigned)nb, 128, 0, s>>>(a);
@@ -166,7 +166,7 @@ int pdx_round_to_f32(const double* in, float* out, int64_t n, void* stream) {
     if (n < 0 || (n > 0 && (!in || !out))) { set_error("pdx_round_to_f32: bad arguments"); return 1; }
     if (n == 0) return 0;
     int64_t nb = (n + 255) / 256;
-    if (nb > 148LL * 32) nb = 148LL * 32;
+    if (nb > (long long)sm_count() * 32) nb = (long long)sm_count() * 32;
     round_to_f32_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(in, out, n);
     count_launch();
     return check_cuda(cudaGetLastError(), "round_to_f32_kernel launch");

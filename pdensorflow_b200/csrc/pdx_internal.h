@@ -9,6 +9,8 @@
 
 namespace pdx {
 
+#define PDX_MAX_DEVICES 64
+
 // Arguments of one fused FD step launch (by value, __grid_constant__).
 struct FdArgs {
     const float* Uin;
@@ -28,6 +30,8 @@ struct FdArgs {
     int yclo, ychi, zclo, zchi;  // same for the y / z axes
     int dxlo, dxhi;              // clamp of plane indices for DIFF (symmetric pad only)
     int x_chunk;                 // planes per CTA (TMA kernel)
+    int nchunk;                  // x-chunks of this launch (set by the launcher)
+    int raster;                  // 1: x-chunks fastest in blockIdx, odd chunks march downwards (pdx_fd_tma.cu)
     int ntz, nty;                // tile counts (TMA kernel)
     int has_x;                   // 0 for 2-D fields
     int dirichlet;
@@ -57,6 +61,8 @@ struct LutArgs {
 void set_error(const std::string& msg);
 int  check_cuda(cudaError_t e, const char* what);
 void count_launch(int64_t n = 1);
+int  sm_count();                       // multiprocessors of the current device (cached per ordinal)
+int  csr_group_hint(const int32_t* rowptr);   // lanes per row registered through pdx_csr_hint, or 0
 
 void fill_model_params(int model, const float* params, float dt, ModelParams* out);
 

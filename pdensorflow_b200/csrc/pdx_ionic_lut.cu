@@ -289,7 +289,7 @@ int lut_model_num_consts(int model) {
 int PDX_LUT_FN(launch_lut_ionic)(int model, const LutArgs& L, int64_t n, const float* U, float* dU, const float* I0,
                                  float* rhs0, cudaStream_t s) {
     int64_t nb = (n + 127) / 128;
-    if (nb > 148 * 32) nb = 148 * 32;
+    if (nb > sm_count() * 32) nb = sm_count() * 32;
     if (nb < 1) nb = 1;
     if (model == PDX_MODEL_CRN) lut_ionic_kernel<PDX_MODEL_CRN, TU_MATH><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);
     else if (model == PDX_MODEL_TTP) lut_ionic_kernel<PDX_MODEL_TTP, TU_MATH><<<(unsigned)nb, 128, 0, s>>>(L, n, U, dU, I0, rhs0);

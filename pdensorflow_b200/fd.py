@@ -8,8 +8,12 @@ CUDA-graph-captured block of steps instead of the reference's Python per-step lo
 (fenton.py:150-159).
 
 ``SlabPartition``/``DistributedFDStepper`` split the slowest axis (reference axis 0) over
-the ranks of a torch.distributed group; one plane of U is exchanged per neighbour per step
-(NCCL send/recv over NVLink), overlapped with the interior planes.
+the ranks of a torch.distributed group.  Default halo path: the step kernel itself stores each
+slab's edge planes into the neighbours' ghost planes over NVLink peer memory (torch symmetric
+memory), one symmetric-memory barrier per step orders the ranks; ``halo='nccl'`` (batched
+send/recv on a side stream, overlapped with the interior planes) is the fallback.
+``FrameStreamer`` is the end-to-end frame loop over HOST buffers (chunked H2D / skewed x-march /
+chunked D2H, all three engines busy on ONE simulation).
 """
 import ctypes as C
 
@@ -108,6 +112,29 @@ class FDStepper:
         self.device = torch.device('cuda' if device is None else device)
         if self.device.type != 'cuda':
             raise L.PdxError('FDStepper needs a CUDA device: there is no CPU path')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        # plans, tensor maps and kernel attributes belong to the CURRENT device: make the stepper's device
+        # current for construction and for every call (a process may drive several GPUs)
+        with torch.cuda.device(self.device):
+            self._init(shape, spacing, dt, diff, model, params, lap, DIFF, math, kernel, part, x_chunk, AVEC, buffers,
+                       dirichlet)
+
+    def _stream(self, stream=None):
+        return L.stream_ptr(torch.cuda.current_stream(self.device) if stream is None else stream)
+
+    def _check_field(self, t, name, extra=()):
+        """Pointers handed to the library are raw: refuse anything that is not a contiguous fp32 tensor of the
+        stepper's array shape on the stepper's device (a bool / float64 / CPU / global-shape mask would be misread)."""
+        L.require_cuda(t, name)
+        if t.device != self.device:
+            raise L.PdxError('%s lives on %s, the stepper on %s' % (name, t.device, self.device))
+        if tuple(t.shape) != tuple(self.array_shape) + tuple(extra):
+            raise L.PdxError('%s has shape %s, expected %s' % (name, tuple(t.shape), tuple(self.array_shape) + tuple(extra)))
+        return t
+
+    def _init(self, shape, spacing, dt, diff, model, params, lap, DIFF, math, kernel, part, x_chunk, AVEC, buffers,
+              dirichlet):
         self.ndim = len(shape)
         if self.ndim not in (2, 3) or len(spacing) != self.ndim:
             raise ValueError('shape/spacing must both be 2-D or 3-D')
@@ -237,17 +264,20 @@ class FDStepper:
     def step(self, nsteps=1, stream=None):
         """nsteps fused steps, one kernel launch each, on the current stream."""
         a, b = self.current_U(), self.other_U()
-        L.check(L.lib().pdx_fd_step(self._plan, L.ptr(a), L.ptr(b), self._states_arr, L.ptr(self.DIFF),
-                                    int(nsteps), L.stream_ptr(stream)))
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pdx_fd_step(self._plan, L.ptr(a), L.ptr(b), self._states_arr, L.ptr(self.DIFF),
+                                        int(nsteps), self._stream(stream)))
         if nsteps & 1:
             self._cur ^= 1
         self.nsteps_done += nsteps
 
-    def step_range(self, xb, xe, stream=None):
-        """Advance only array planes [xb, xe) from current_U into other_U (no buffer swap)."""
-        L.check(L.lib().pdx_fd_step_range(self._plan, L.ptr(self.current_U()), L.ptr(self.other_U()),
-                                          self._states_arr, L.ptr(self.DIFF), int(xb), int(xe),
-                                          L.stream_ptr(stream)))
+    def step_range(self, xb, xe, stream=None, reverse=False):
+        """Advance only array planes [xb, xe) from current_U into other_U (no buffer swap); ``reverse`` reads
+        other_U and writes current_U (the odd steps of a skewed multi-step march, see FrameStreamer)."""
+        a, b = (self.other_U(), self.current_U()) if reverse else (self.current_U(), self.other_U())
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pdx_fd_step_range(self._plan, L.ptr(a), L.ptr(b), self._states_arr, L.ptr(self.DIFF),
+                                              int(xb), int(xe), self._stream(stream)))
 
     def swap(self):
         self._cur ^= 1
@@ -259,15 +289,16 @@ class FDStepper:
             raise ValueError('captured blocks use an even number of steps (ping-pong parity)')
         key = (nsteps, self._cur)
         if key not in self._graphs:
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream(device=self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s):
-                a, b = self.current_U(), self.other_U()
-                with torch.cuda.graph(g, stream=s):
-                    L.check(L.lib().pdx_fd_step(self._plan, L.ptr(a), L.ptr(b), self._states_arr,
-                                                L.ptr(self.DIFF), int(nsteps), L.stream_ptr(s)))
-            torch.cuda.current_stream(self.device).wait_stream(s)
+            with torch.cuda.device(self.device):
+                g = torch.cuda.CUDAGraph()
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    a, b = self.current_U(), self.other_U()
+                    with torch.cuda.graph(g, stream=s):
+                        L.check(L.lib().pdx_fd_step(self._plan, L.ptr(a), L.ptr(b), self._states_arr,
+                                                    L.ptr(self.DIFF), int(nsteps), L.stream_ptr(s)))
+                torch.cuda.current_stream(self.device).wait_stream(s)
             self._graphs[key] = g
             self._captured_launches += nsteps
         return self._graphs[key]
@@ -282,8 +313,9 @@ class FDStepper:
         nblk, rem = divmod(nsteps, block)
         if nblk:
             g = self.capture(block)
-            for _ in range(nblk):
-                g.replay()
+            with torch.cuda.device(self.device):
+                for _ in range(nblk):
+                    g.replay()
             self.nsteps_done += nblk * block
             self.graph_kernel_launches += nblk * block     # one kernel node per captured step
         if rem:
@@ -291,10 +323,13 @@ class FDStepper:
 
     def apply_stimulus(self, mask, intensity, stream=None, everywhere=False):
         """U = where(mask, max(U, intensity*mask), U): Tests/FD/Fenton/fenton.py:154-156; ``everywhere=True`` is the
-        heat examples' U = maximum(U, intensity*mask) on every node (Tests/FD/HeatEquation/heat.py:143-144)."""
+        heat examples' U = maximum(U, intensity*mask) on every node (Tests/FD/HeatEquation/heat.py:143-144).
+        ``mask`` is a contiguous fp32 CUDA tensor of the stepper's array shape (ghost planes included for slabs)."""
         U = self.current_U()
+        self._check_field(mask, 'stimulus mask')
         fn = L.lib().pdx_stim_apply_max if everywhere else L.lib().pdx_stim_apply
-        L.check(fn(L.ptr(U), L.ptr(mask), float(np.float32(intensity)), U.numel(), L.stream_ptr(stream)))
+        with torch.cuda.device(self.device):
+            L.check(fn(L.ptr(U), L.ptr(mask), float(np.float32(intensity)), U.numel(), self._stream(stream)))
 
     def launches(self):
         """Kernel launches issued for this stepper: direct ones plus graph-replayed nodes
@@ -415,6 +450,152 @@ class DistributedFDStepper:
 
     def owned_U(self):
         return self.part.owned(self.fd.current_U())
+
+
+def numa_local_pinned(shape, device, dtype=torch.float32):
+    """Pinned host tensor whose pages sit on the NUMA node the GPU hangs off (Linux first-touch policy: the
+    allocating thread is bound to that node's CPUs while cudaHostAlloc populates the pages).  On a box with a single
+    node, or without the sysfs entries, this is a plain pinned allocation."""
+    import os
+    old = None
+    try:
+        idx = torch.device(device).index
+        idx = torch.cuda.current_device() if idx is None else idx
+        bus = torch.cuda.get_device_properties(idx).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(idx), 'pci_domain_id', 0)
+        dev_id = getattr(torch.cuda.get_device_properties(idx), 'pci_device_id', 0)
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0' % (dom, bus, dev_id)
+        with open(path + '/numa_node') as f:
+            node = int(f.read().strip())
+        if node >= 0:
+            with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+                cpus = set()
+                for part in f.read().strip().split(','):
+                    a, _, b = part.partition('-')
+                    cpus.update(range(int(a), int(b or a) + 1))
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed:
+                old = allowed
+                os.sched_setaffinity(0, cpus & allowed)
+    except Exception:
+        old = None
+    try:
+        t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        t.zero_()                      # touch every page while bound
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
+    return t
+
+
+class FrameStreamer:
+    """End-to-end frame loop of ONE simulation over HOST buffers with all three engines busy.
+
+    A frame is what the reference examples do between two writer calls (``Tests/FD/Fenton/fenton.py:150-159``:
+    ``dt_per_plot`` steps, then the potential goes to the writer) with the potential living in pinned HOST memory
+    between frames: upload U, advance ``steps`` fused steps, download U.  The x axis (slowest, contiguous planes) is
+    cut into ``nchunks`` chunks and the three phases are pipelined chunk by chunk:
+
+    * H2D stream: chunk k of the frame's input goes up as soon as the previous frame's download has released
+      the host planes it reads (chunk k+1 of that frame);
+    * compute stream, ``skew=True``: a time-skewed march - once planes [0, B_k) are on the device, step s may advance
+      planes below B_k - s (step s at plane x needs step s-1 at x-1..x+1), so every arriving chunk triggers ``steps``
+      range launches ``pdx_fd_step_range`` on shifted plane windows, ping-ponging between the two U buffers in
+      place; the last chunk runs every step to the end of the grid.  ``skew=False``: all steps after the last chunk
+      (``advance`` callback - the slab-decomposed stepper, whose halo protocol wants whole-slab launches);
+    * D2H stream: the planes a chunk's last step completed go down at once.
+
+    Results are bitwise those of ``steps`` whole-grid launches (tests/test_fd_gpu.py).  Frame time -> the PCIe time
+    of one direction instead of H2D + compute + D2H.
+    """
+
+    def __init__(self, stepper, steps=10, nchunks=8, skew=True, advance=None, planes=None):
+        if steps % 2:
+            raise ValueError('frames use an even number of steps (ping-pong parity)')
+        self.fd, self.steps, self.skew, self.advance = stepper, int(steps), bool(skew), advance
+        dev = stepper.device
+        # planes [x0, x1) of the array are the ones that travel (a slab leaves its ghost planes out)
+        self.x0, self.x1 = planes if planes is not None else (0, stepper.array_shape[0])
+        n = self.x1 - self.x0
+        if stepper.ndim != 3:
+            raise ValueError('FrameStreamer streams 3-D grids plane by plane')
+        if skew:
+            if stepper.part is not None:
+                raise ValueError('the time-skewed march needs a stand-alone grid (use skew=False for slabs)')
+            nchunks = max(1, min(int(nchunks), n // (self.steps + 2)))
+        else:
+            nchunks = max(1, min(int(nchunks), n))
+        self.bounds = [self.x0 + (n * k) // nchunks for k in range(nchunks + 1)]
+        self.nchunks = nchunks
+        self.h2d, self.comp, self.d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.host = numa_local_pinned(stepper.array_shape, dev)
+        self.host.copy_(stepper.U())
+        torch.cuda.synchronize(dev)
+        self._up = [torch.cuda.Event() for _ in range(nchunks)]
+        self._fin = [torch.cuda.Event() for _ in range(nchunks)]
+        self._down = [torch.cuda.Event() for _ in range(nchunks)]
+        self._first = True
+        self.frame_bytes = n * stepper.array_shape[1] * stepper.array_shape[2] * 4
+        self.launches_per_frame = self.steps * (nchunks if skew else 1)
+
+    def _limit(self, s, k):
+        """Planes below this index have their step-s value once chunk k is on the device."""
+        return self.x1 if k == self.nchunks - 1 else self.bounds[k + 1] - s
+
+    def frame(self):
+        """One frame (enqueue only; ``wait()`` or an event orders the host)."""
+        fd, S, C, b = self.fd, self.steps, self.nchunks, self.bounds
+        A = fd.current_U()
+        for k in range(C):
+            with torch.cuda.stream(self.h2d):
+                if not self._first:      # the host planes hold the previous frame once its download got there
+                    self.h2d.wait_event(self._down[min(k + 1, C - 1)])
+                A[b[k]:b[k + 1]].copy_(self.host[b[k]:b[k + 1]], non_blocking=True)
+                self._up[k].record(self.h2d)
+            if self.skew:
+                with torch.cuda.stream(self.comp):
+                    self.comp.wait_event(self._up[k])
+                    for s in range(1, S + 1):
+                        lo = self.x0 if k == 0 else self._limit(s, k - 1)
+                        hi = self._limit(s, k)
+                        if hi > lo:
+                            fd.step_range(lo, hi, stream=self.comp, reverse=(s % 2 == 0))
+                    self._fin[k].record(self.comp)
+                self._download(k, A)
+        if not self.skew:
+            with torch.cuda.stream(self.comp):
+                self.comp.wait_event(self._up[C - 1])
+                if self.advance is not None:
+                    self.advance(S)
+                else:
+                    fd.step(S, stream=self.comp)
+                A = fd.current_U()
+                self._fin[0].record(self.comp)
+            for k in range(C):
+                self._download(k, A, fin=self._fin[0])
+        else:
+            fd.nsteps_done += S
+        self._first = False
+
+    def _download(self, k, A, fin=None):
+        S, C, b = self.steps, self.nchunks, self.bounds
+        if self.skew:
+            lo = self.x0 if k == 0 else self._limit(S, k - 1)
+            hi = self._limit(S, k)
+        else:
+            lo, hi = b[k], b[k + 1]
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self._fin[k] if fin is None else fin)
+            if hi > lo:
+                self.host[lo:hi].copy_(A[lo:hi], non_blocking=True)
+            self._down[k].record(self.d2h)
+
+    def wait(self):
+        for st in (self.h2d, self.comp, self.d2h):
+            st.synchronize()
 
 
 class FramePipeline:

@@ -123,6 +123,8 @@ class PartitionedExplicitFEM:
         self.rowptr = torch.from_numpy(rowptr).to(dev)
         self.col = torch.from_numpy(col).to(dev)
         self.kval = torch.from_numpy(np.ascontiguousarray(kval, dtype=np.float32)).to(dev)
+        if layout == 'csr':
+            L.check(L.lib().pdx_csr_hint(L.ptr(self.rowptr), self.nloc, self.nnz))     # lanes per row of the CSR kernel
         self.mlinv = torch.from_numpy((1.0 / np.asarray(mlump, dtype=np.float64)).astype(np.float32)).to(dev)
         self.model_id = _MODEL_IDS[model]
         self.math_id = _MATH_IDS[math]

@@ -39,6 +39,8 @@ class CSRMatrix:
             dev = B.device()
             self._dev = (torch.from_numpy(self.rowptr).to(dev), torch.from_numpy(self.col).to(dev),
                          torch.from_numpy(self.val).to(dev))
+            # lanes-per-row of the CSR kernels come from nnz / n: registered once here, never read back from the device
+            L.check(L.lib().pdx_csr_hint(L.ptr(self._dev[0]), self.n, self.nnz))
         return self._dev
 
     def to_scipy(self):

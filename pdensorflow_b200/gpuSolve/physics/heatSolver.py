@@ -160,7 +160,10 @@ class HeatSolver:
             for key, stim in self._StimulusDict.items():
                 if stim.stimulate_tissue_timevalue(t32):
                     active.append(key)
-        k = tuple(active)
+        # the reference recomputes intensity*mask every step: key the cached field on everything it depends on
+        # (set_intensity / set_stimregion / apply_indices_permutation replace the value or the mask tensor)
+        k = tuple((key, float(self._StimulusDict[key].intensity()), self._StimulusDict[key].get_stimregion().data_ptr())
+                  for key in active)
         I0 = self._I0_cache.get(k)
         if I0 is None:
             I0 = torch.zeros_like(self._U)

@@ -311,3 +311,87 @@ def test_index_arithmetic_beyond_2_31_nodes(cuda, kernel):
     torch.cuda.empty_cache()
     small = run(48)
     assert torch.equal(small.U()[16:20], keep)
+
+
+# ------------------------------------------------------------------------------ round 2: rasterisation, streamer
+@pytest.mark.parametrize('lap', ['homog', 'heterog'])
+def test_cta_rasterisation_is_invisible(cuda, lap, monkeypatch):
+    """PDX_FD_RASTER=1 (x-chunks fastest, odd chunks marched downwards) must give the bits of the plain
+    layer-by-layer order for every chunk length, incl. ragged last chunks and the mirrored x neighbours of the
+    heterogeneous operator."""
+    from pdensorflow_b200.fd import FDStepper
+    shape = (45, 24, 132)
+    U, states = random_fields(shape, seed=31)
+    DIFFa = np.random.default_rng(5).uniform(0.2, 1.0, size=shape).astype(np.float32) if lap == 'heterog' else None
+    res = {}
+    for raster in ('0', '1'):
+        monkeypatch.setenv('PDX_FD_RASTER', raster)
+        for chunk in (0, 3, 8):
+            st = FDStepper(shape, (1.0, 0.9, 1.1), 0.05, 0.8, model='fenton4v', math='exact', kernel='tma', x_chunk=chunk,
+                           lap=lap, DIFF=DIFFa)
+            st.set_U(U); st.set_states(states); st.step(3)
+            res[(raster, chunk)] = (st.U().cpu().numpy(), [s.cpu().numpy() for s in st.states])
+    ref = res[('0', 0)]
+    for key, (Ug, sg) in res.items():
+        assert np.array_equal(Ug, ref[0]), key
+        for a, b in zip(sg, ref[1]):
+            assert np.array_equal(a, b), key
+
+
+@pytest.mark.parametrize('steps,nchunks', [(2, 3), (6, 4), (10, 2), (10, 8)])
+def test_frame_streamer_equals_whole_grid_steps(cuda, steps, nchunks):
+    """fd.FrameStreamer (chunked H2D -> time-skewed range launches -> chunked D2H, single simulation living in
+    pinned host memory) must reproduce, bitwise, whole-grid launches of the same number of steps, frame after frame."""
+    from pdensorflow_b200.fd import FDStepper, FrameStreamer
+    shape = (70, 24, 128)
+    U, states = random_fields(shape, seed=37)
+    ref = FDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8, model='fenton4v', math='exact')
+    ref.set_U(U); ref.set_states(states)
+    st = FDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8, model='fenton4v', math='exact')
+    st.set_U(U); st.set_states(states)
+    fs = FrameStreamer(st, steps, nchunks=nchunks)
+    assert fs.nchunks == min(nchunks, shape[0] // (steps + 2))
+    for frame in range(3):
+        fs.frame()
+        ref.step(steps)
+        if frame == 1:
+            fs.wait()              # draining between frames must not matter
+    fs.wait()
+    torch.cuda.synchronize()
+    assert torch.equal(st.U(), ref.U())
+    assert np.array_equal(fs.host.numpy(), ref.U().cpu().numpy())
+    for a, b in zip(st.states, ref.states):
+        assert torch.equal(a, b)
+
+
+def test_frame_streamer_unskewed_slab_mode(cuda):
+    """skew=False (the multi-GPU frame loop: whole-slab steps between the chunked copies) on a stand-alone grid."""
+    from pdensorflow_b200.fd import FDStepper, FrameStreamer
+    shape = (33, 16, 128)
+    U, states = random_fields(shape, seed=41)
+    ref = FDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8, model='fenton4v', math='exact')
+    ref.set_U(U); ref.set_states(states)
+    st = FDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8, model='fenton4v', math='exact')
+    st.set_U(U); st.set_states(states)
+    fs = FrameStreamer(st, 4, nchunks=5, skew=False)
+    for _ in range(3):
+        fs.frame()
+        ref.step(4)
+    fs.wait()
+    assert torch.equal(st.U(), ref.U()) and np.array_equal(fs.host.numpy(), ref.U().cpu().numpy())
+
+
+def test_raw_pointer_arguments_are_checked(cuda):
+    """masks reach the kernel as raw pointers - wrong dtype / device / shape must raise, not misread."""
+    from pdensorflow_b200 import _lib as L
+    from pdensorflow_b200.fd import FDStepper
+    shape = (8, 8, 16)
+    st = FDStepper(shape, (1.0, 1.0, 1.0), 0.1, 0.8)
+    st.set_U(plane_wave_ic(shape))
+    good = torch.ones(shape, device='cuda')
+    st.apply_stimulus(good, 60.0)
+    for bad in (torch.ones(shape, device='cuda', dtype=torch.bool), torch.ones(shape, device='cuda', dtype=torch.float64),
+                torch.ones(shape), torch.ones((8, 8, 8), device='cuda'), torch.ones((16, 8, 8), device='cuda').permute(2, 1, 0)):
+        with pytest.raises(L.PdxError):
+            st.apply_stimulus(bad, 60.0)
+    assert float(st.U().min()) == 60.0

@@ -1,6 +1,6 @@
 """Tests/FEM/HeatEquation/heat.py replayed on the mirror's HeatSolver against the fixture frozen from the reference source
 (tests/golden/ref_heat.npz femheat_*; the oracle reproduces it on CPU: tests/test_ref_golden_cpu.py::
-test_heat_solver_vs_reference_source).  Parked: written with no GPU time left to run it."""
+test_heat_solver_vs_reference_source)."""
 import os
 import pickle
 
@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def test_heat_solver_vs_reference_source(cuda, tmp_path):
     from pdensorflow_b200.gpuSolve.physics import HeatSolver
-    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'golden', 'ref_heat.npz'))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_heat.npz'))
     pts, trias, fib = g['femheat_pts'], g['femheat_Trias'], g['femheat_fibres']
     fn = str(tmp_path / 'sq.pkl')
     with open(fn, 'wb') as f:

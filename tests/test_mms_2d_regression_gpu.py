@@ -1,14 +1,14 @@
 """Tests/CICD/nightly/test_mms_2d_regression.py:50-184 transcribed to the mirror (MonodomainSolver + ModifiedMS2v on a
 2-D sheet: planar front, monotone activation, conduction velocity within 10 % of the analytic Nagumo speed).  The
 oracle passes it on CPU (tests/test_fem_oracle_cpu.py::test_reference_mms_2d_regression_on_the_oracle); the 1-D
-sibling already runs on the GPU in tests/test_fem_gpu.py.  Parked: written with no GPU time left to run it."""
+sibling already runs on the GPU in tests/test_fem_gpu.py."""
 import os
 import sys
 
 import numpy as np
 import pytest
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from test_fem_gpu import _local_activation_times  # noqa: E402
 
 pytestmark = pytest.mark.gpu
