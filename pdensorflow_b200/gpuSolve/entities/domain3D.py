@@ -2,9 +2,9 @@
 geometry mask, conductivity field, fibre dyadic) that feeds ``laplace_heterog`` / ``laplace_heterog_aniso``
 (SURVEY.md section 8f, N4).  Host container over NumPy arrays, as in the reference.
 
-The ``assign_*`` path (what Tests/FD/Fenton_sphere/fenton.py:86-101 uses) and the file-less defaults are complete.
-``load_*`` read ``.npy`` arrays; PNG-mosaic / NIfTI images go through the reference's ImageData reader, which needs
-imageio / nibabel and is outside the time-stepping scope.
+``assign_*`` is what Tests/FD/Fenton_sphere/fenton.py:86-101 uses; ``load_*`` read PNG mosaics (Mx x My grid of
+slices, Tests/FD/Fenton_atria/fenton.py:88-89), NIfTI-1 and ``.npy`` files through ``gpuSolve.IO.readers.imagedata``
+(standard-library decoders; the reference needs imageio / nibabel).
 """
 import sys
 import time
@@ -12,11 +12,11 @@ import time
 import numpy as np
 
 
-def _load_voxels(fname):
-    if not str(fname).endswith('.npy'):
-        raise NotImplementedError('pdensorflow_b200 reads .npy voxel files; PNG-mosaic / NIfTI images need the '
-                                  'reference\'s ImageData reader (out of scope, SURVEY.md section 2)')
-    return np.load(fname)
+def _load_image(fname, Mx, My):
+    from ..IO.readers.imagedata import ImageData
+    image = ImageData()
+    image.load_image(fname, Mx, My)
+    return image
 
 
 class Domain3D:
@@ -47,11 +47,12 @@ class Domain3D:
         if self._geometryfile == '':
             self._geometryfile = fname
         if len(self._geometryfile):
-            vox = np.asarray(_load_voxels(self._geometryfile), dtype=np.float64)
-            lo, hi = vox.min(), vox.max()
-            vox = (vox - lo) / (hi - lo) if hi > lo else np.zeros_like(vox)          # 'unit' rescaling
+            print('reading the geometry from the file {0}'.format(fname))
+            vox = _load_image(self._geometryfile, Mx, My).get_rescaled_data('unit')   # (x - min) / (max - min), float64
             self._width, self._height, self._depth = vox.shape
-            self.__geometry = np.where(vox > threshold, 1.0, 0.0)
+            vox[vox > threshold] = 1.0                                           # domain3D.py:56-58
+            vox[vox <= threshold] = 0.0
+            self.__geometry = vox
             print('Sizes: ({}X{}X{})'.format(self._width, self._height, self._depth))
         else:
             print('Cubic geometry ({}X{}X{})'.format(self._width, self._height, self._depth))
@@ -86,7 +87,8 @@ class Domain3D:
             sys.exit("No geometry defined! (assign a geometry first)")
         then = time.time()
         if len(self._conductivityfile):
-            self.__set_conductivity(np.asarray(_load_voxels(self._conductivityfile), dtype=np.float64))
+            print('reading the conductivity from the file {0}'.format(fname))
+            self.__set_conductivity(_load_image(self._conductivityfile, Mx, My).get_fdata())
         else:
             print('homogeneous conductivity')
             self.__conductivity = cond_unif * self.__geometry
@@ -109,7 +111,8 @@ class Domain3D:
         if not len(self._fibtensorfile):
             sys.exit("Invalid fiber file!")
         then = time.time()
-        v = np.asarray(_load_voxels(self._fibtensorfile), dtype=np.float64)
+        print('reading the fibres from the file {0}'.format(fname))
+        v = _load_image(self._fibtensorfile, Mx, My).get_fdata()
         W, H, D, _ = v.shape
         fibtens = np.zeros(shape=(W, H, D, 6))
         for c, (a, b) in enumerate(((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))):

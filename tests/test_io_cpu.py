@@ -176,8 +176,17 @@ def test_domain3d_voxel_files(tmp_path):
     T = d.fibtensor()
     assert T.shape == (4, 3, 5, 6)
     assert np.array_equal(T[..., 1], fib[..., 0] * fib[..., 1]) and np.array_equal(T[..., 5], fib[..., 2] ** 2)
-    with pytest.raises(NotImplementedError):
-        Domain3D().load_geometry_file('atria.png', 10, 10)
+    # PNG mosaic (Tests/FD/Fenton_atria/fenton.py:88-89): 6 slices of 4 x 3 voxels on a 3 x 2 grid
+    from pdensorflow_b200.gpuSolve.IO.readers.imagedata import volume_to_mosaic, write_png_gray
+    vol = rng.integers(0, 255, size=(4, 3, 6)).astype(np.uint8)
+    vol[0, 0, 0], vol[1, 1, 1] = 0, 255
+    write_png_gray(str(tmp_path / 'atria.png'), volume_to_mosaic(vol, 3, 2))
+    dp = Domain3D()
+    dp.load_geometry_file(str(tmp_path / 'atria.png'), 3, 2, threshold=0.25)
+    assert (dp.width(), dp.height(), dp.depth()) == (4, 3, 6)
+    assert np.array_equal(dp.geometry(), (vol / 255.0 > 0.25).astype(float))
+    with pytest.raises(ValueError):
+        Domain3D().load_geometry_file(str(tmp_path / 'atria.png'), 5, 2)            # not a 5 x 2 mosaic
 
 
 def test_reference_basewriter_unit_tests(tmp_path):

@@ -407,3 +407,37 @@ def test_monodomain_solver_vs_reference_source(cuda, tag, tmp_path):
     ref = g[tag + '_frames']
     for k in range(ref.shape[0]):
         assert rel_l2(frames[k], ref[k]) <= 5e-5, (k, rel_l2(frames[k], ref[k]))
+
+
+# ------------------------------------------------------------------------------ N4: anatomical example from a PNG mosaic
+@pytest.mark.parametrize('math', ['exact', 'fast'])
+def test_atria_example_vs_reference_source(cuda, math):
+    """Tests/FD/Fenton_atria/fenton.py run() end to end on the fused heterogeneous kernel: the 128^3 anatomy comes from
+    the PNG mosaic through ImageData -> Domain3D (standard-library decoder), DIFF = 0.75 * geometry, initial excited
+    slab, the all-ones S2 quirk at step 50; frames i = 0, 40, 80 against the reference run from source."""
+    from test_atria_cpu import atria_setup
+    from pdensorflow_b200.fd import FDStepper
+    from pdensorflow_b200.gpuSolve.entities import Domain3D
+    from pdensorflow_b200.gpuSolve.force_terms import Stimulus
+    g = gold('ref_atria.npz')
+    dom, mask, U, s2_init, dt, per_plot, samples, s2_time = atria_setup(g, Domain3D)
+    st = FDStepper(U.shape, (dom.dx(), dom.dy(), dom.dz()), dt, 1.0, model='fenton4v', lap='heterog',
+                   DIFF=dom.conductivity().astype(np.float32), math=math)
+    assert st.kernel == 'tma'
+    st.set_U(U)
+    s2 = Stimulus({'tstart': s2_time, 'nstim': 1, 'period': 800, 'duration': dt, 'dt': dt, 'intensity': 60.0})
+    s2.set_stimregion(s2_init)
+    frames, fired = [U.copy()], []
+    for i in range(samples):
+        st.step(1)
+        if s2.stimulate_tissue_timestep(i, dt):
+            st.apply_stimulus(s2.get_stimregion(), s2.intensity())
+            fired.append(i)
+        if i % per_plot == 0:
+            frames.append(np.where(mask, host(st.U()), np.float32(-1.0)).astype(np.float32))
+    ref = g['frames']
+    assert fired == [50] and len(frames) == ref.shape[0] == 4
+    tol = 1e-6 if math == 'exact' else 1e-5
+    for k in range(4):
+        assert rel_l2(frames[k], ref[k]) <= tol, (k, rel_l2(frames[k], ref[k]))
+    assert rel_l2(host(st.states[0]), g['V_end']) <= 10 * tol
