@@ -347,9 +347,12 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     p->base.nty = (d.ny + ty - 1) / ty;
     p->base.ntz = (d.nz + tz - 1) / tz;
     p->base.x_chunk = d.x_chunk > 0 ? d.x_chunk : fd_tma_auto_chunk(d);
-    {   // CTA rasterisation of the TMA kernel (pdx_fd_tma.cu): 1 = x-chunks fastest, alternating march direction
-        const char* e = std::getenv("PDX_FD_RASTER");           // A/B switch
-        p->base.raster = (e && e[0] == '0') ? 0 : 1;
+    {   // CTA rasterisation of the TMA kernel (pdx_fd_tma.cu): tile groups + alternating march direction once an
+        // x-layer of CTAs is many waves (its halo planes would fall out of L2); PDX_FD_RASTER=<G> overrides (0 = off)
+        const char* e = std::getenv("PDX_FD_RASTER");
+        const long long layer = (long long)p->base.ntz * p->base.nty;
+        p->base.raster = e ? std::atoi(e) : (layer > 1024 ? 16 : 0);
+        if (p->base.raster < 0) p->base.raster = 0;
     }
     if (kernel == PDX_KERNEL_TMA) {
         // set the kernel's shared-memory attribute now (an empty range launches nothing), so

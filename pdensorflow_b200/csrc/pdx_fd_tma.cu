@@ -120,23 +120,37 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
     unsigned char* sring = smem + NSTAGE * G::SLOT_BYTES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // Rasterisation.  raster 0: tiles fastest, x-chunks slowest (an x-layer of CTAs at a time).
-    // raster 1 (3-D): x-chunks fastest, and odd chunks march DOWNWARDS: the resident set then holds every
-    // chunk of a few tiles, neighbouring chunks start together at their shared planes (c even: planes
-    // 8c+7, 8c+8) and meet again at the other pair when they finish, so the two halo planes a chunk
-    // re-reads are in L2 whatever the plane size (a 2048^2 layer of CTAs is 9 waves: its halo planes
-    // are long evicted when the next layer runs).
-    int b = blockIdx.x, chunk;
-    if (HAS_X && a.raster) { chunk = b % a.nchunk; b /= a.nchunk; }
-    const int tz = b % a.ntz;  b /= a.ntz;
-    const int ty = b % a.nty;  b /= a.nty;
-    if (!(HAS_X && a.raster)) chunk = b;
+    // Rasterisation.  raster 0: tiles fastest, x-chunks slowest (an x-layer of CTAs at a time): right when a layer
+    // is a wave or two of CTAs, because the two halo planes a chunk re-reads are then still in L2 (512^3: DRAM
+    // reads 1.006 x algorithmic).  A 2048^2 layer is 9 waves and its halo planes are long evicted when the next
+    // layer runs (ncu: reads 1.067 x).  raster G > 0 (3-D): groups of G consecutive tiles (z fastest, so a group
+    // reads contiguous rows - DRAM page locality), inside a group the x-chunks come next and odd chunks march
+    // DOWNWARDS: the resident set holds every chunk of a few tile groups, neighbouring chunks start together at
+    // their shared planes and meet again at the other pair when they finish (reads 1.018 x).
+    int b = blockIdx.x, chunk, tz, ty;
+    if (HAS_X && a.raster > 0) {
+        const int G = a.raster;
+        const int ntile = a.ntz * a.nty;
+        const int per_group = G * a.nchunk;
+        const int grp = b / per_group;
+        const int g0 = grp * G;
+        const int gsz = min(G, ntile - g0);              // the last group may be short
+        const int r = b - grp * per_group;
+        chunk = r / gsz;
+        const int t = g0 + (r - chunk * gsz);
+        tz = t % a.ntz;
+        ty = t / a.ntz;
+    } else {
+        tz = b % a.ntz;  b /= a.ntz;
+        ty = b % a.nty;  b /= a.nty;
+        chunk = b;
+    }
     const int z0 = tz * TZ, y0 = ty * TY;
     const int xb = a.xb + chunk * a.x_chunk;
     const int xe = min(xb + a.x_chunk, a.xe);
     const int np = xe - xb;
     const int nlog = HAS_X ? np + 2 : np;           // logical planes q = xb-1 .. xe (3-D)
-    const bool down = HAS_X && a.raster && (chunk & 1);   // CTA uniform
+    const bool down = HAS_X && a.raster > 0 && (chunk & 1);   // CTA uniform
     const int qs = down ? -1 : 1;                   // logical plane j is array plane q0 + qs*j
     const int q0 = HAS_X ? (down ? xe : xb - 1) : xb;
     const int p0 = down ? xe - 1 : xb;              // i-th plane advanced: p0 + qs*i

@@ -31,7 +31,7 @@ struct FdArgs {
     int dxlo, dxhi;              // clamp of plane indices for DIFF (symmetric pad only)
     int x_chunk;                 // planes per CTA (TMA kernel)
     int nchunk;                  // x-chunks of this launch (set by the launcher)
-    int raster;                  // 1: x-chunks fastest in blockIdx, odd chunks march downwards (pdx_fd_tma.cu)
+    int raster;                  // G > 0: tile groups of G, x-chunks next, odd chunks march downwards (pdx_fd_tma.cu)
     int ntz, nty;                // tile counts (TMA kernel)
     int has_x;                   // 0 for 2-D fields
     int dirichlet;

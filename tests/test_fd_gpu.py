@@ -316,15 +316,15 @@ def test_index_arithmetic_beyond_2_31_nodes(cuda, kernel):
 # ------------------------------------------------------------------------------ round 2: rasterisation, streamer
 @pytest.mark.parametrize('lap', ['homog', 'heterog'])
 def test_cta_rasterisation_is_invisible(cuda, lap, monkeypatch):
-    """PDX_FD_RASTER=1 (x-chunks fastest, odd chunks marched downwards) must give the bits of the plain
-    layer-by-layer order for every chunk length, incl. ragged last chunks and the mirrored x neighbours of the
-    heterogeneous operator."""
+    """PDX_FD_RASTER=G (tile groups of G, x-chunks next, odd chunks marched downwards) must give the bits of the
+    plain layer-by-layer order for every group size and chunk length, incl. short last groups, ragged last chunks and
+    the mirrored x neighbours of the heterogeneous operator."""
     from pdensorflow_b200.fd import FDStepper
     shape = (45, 24, 132)
     U, states = random_fields(shape, seed=31)
     DIFFa = np.random.default_rng(5).uniform(0.2, 1.0, size=shape).astype(np.float32) if lap == 'heterog' else None
     res = {}
-    for raster in ('0', '1'):
+    for raster in ('0', '1', '4', '16'):          # 3 y-tiles x 2 z-tiles = 6 tiles: groups of 1, 4 + 2, and one short group
         monkeypatch.setenv('PDX_FD_RASTER', raster)
         for chunk in (0, 3, 8):
             st = FDStepper(shape, (1.0, 0.9, 1.1), 0.05, 0.8, model='fenton4v', math='exact', kernel='tma', x_chunk=chunk,

@@ -12,9 +12,9 @@ def timeit(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 shapes = ((512, 512, 512), (128, 2048, 2048))
-chunks = tuple(int(c) for c in (sys.argv[1].split(',') if len(sys.argv) > 1 else '4,6,8,12,16,32,64'.split(',')))
+chunks = tuple(int(c) for c in (sys.argv[1].split(',') if len(sys.argv) > 1 else '6,8,12'.split(',')))
 for G in shapes:
-    for raster in ('0', '1'):
+    for raster in ('0', '4', '16', '64'):
         os.environ['PDX_FD_RASTER'] = raster
         for chunk in chunks:
             st = FDStepper(G, (1., 1., 1.), 0.1, 0.8, x_chunk=chunk)
