@@ -54,8 +54,8 @@ def test_pointwise_tile_kernel_equals_scalar_kernel(cuda, tag, n, monkeypatch):
     for x, y in zip(a, b):
         assert np.isfinite(x).all() and np.array_equal(x, y)
     fa = _pointwise(tag, n, 'fast', True, monkeypatch)
-    for x, y in zip(fa, a):                                # FAST: fp32 expf/logf + contraction
-        np.testing.assert_allclose(x, y, rtol=3e-5, atol=1e-6 * max(np.abs(y).max(), 1e-30))
+    for x, y in zip(fa, a):            # FAST: fp32 expf/logf, approximate division, FMA contraction (a concentration
+        assert rel_l2(x, y) <= 1e-4    # increment is a difference of large currents: compare arrays, not elements)
 
 
 @pytest.mark.parametrize('tag', ['crn', 'ttp'])
