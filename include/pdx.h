@@ -358,6 +358,20 @@ int pdx_fem_assemble(int nv, int64_t ne, const int32_t* elems, int elem_stride, 
                      double* mass_acc, double* stiff_acc, int32_t* status, void* stream);
 int pdx_round_to_f32(const double* in, float* out, int64_t n, void* stream);
 
+/* ---- matrix-format and ghost plumbing on the device (the reference does all of it on the
+ * host: gpuSolve/matrices/globalMatrices.py:54-74,612-675, and has no multi-GPU path) -------------------------------
+ * CSR -> SELL-32 (the layout of pdx_fem_explicit_step_sell / pdx_pcg_part with sell = 1): pdx_sell_slice_widths writes
+ * the longest row of every 32-row slice; the caller forms slice_ptr = exclusive scan of 32 * width (int32) and
+ * allocates slice_ptr[nslices] entries; pdx_sell_fill scatters the rows column-major into their slices and pads with
+ * (col = row_lo + own row, val = 0).  rowptr is local (n + 1), col is copied verbatim. */
+int pdx_sell_slice_widths(int32_t n, const int32_t* rowptr, int32_t* widths /* ceil(n / 32) */, void* stream);
+int pdx_sell_fill(int32_t n, int32_t row_lo, const int32_t* rowptr, const int32_t* col, const float* val,
+                  const int32_t* slice_ptr, int32_t* scol, float* sval, void* stream);
+/* General ghost exchange of a partitioned step: peer_bufs[peer[i]][rows[i]] = src[rows[i]] for i < count.  peer_bufs
+ * is a DEVICE array of the ranks' full-length buffers (NVLink peer mappings); rows are global indices. */
+int pdx_push_rows(const float* src, int32_t count, const int32_t* rows, const int32_t* peer, float* const* peer_bufs,
+                  void* stream);
+
 /* ------------------------------------------------------------------ misc */
 int         pdx_version(void);
 const char* pdx_last_error(void);

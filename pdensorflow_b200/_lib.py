@@ -102,6 +102,9 @@ _SIGNATURES = {
                                              _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
     'pdx_fem_assemble': (C.c_int, [C.c_int, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'pdx_round_to_f32': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'pdx_sell_slice_widths': (C.c_int, [C.c_int32, _P, _P, _P]),
+    'pdx_sell_fill': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    'pdx_push_rows': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     'pdx_pcg_part_workspace_bytes': (C.c_int64, [C.c_int32]),
     'pdx_pcg_part_create': (C.c_int, [C.POINTER(PcgPartDesc), C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
     'pdx_pcg_part_destroy': (None, [_P]),

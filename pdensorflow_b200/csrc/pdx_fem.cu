@@ -44,6 +44,7 @@ struct PcgArgs {
     const float* rhs0;
     float* x;
     float *r, *p, *q;       // work vectors
+    float* p2;              // second direction buffer (the direction update is folded into the SpMV)
     float* part;            // 3 * gridDim.x partial sums
     int maxiter;
     int check_every;
@@ -93,19 +94,45 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
 
     int niters = 0;
     int flags = 0;
+    // TWO grid barriers per iteration.  The direction update p_k = z_{k-1} + beta_{k-1} p_{k-1} (conjgrad.py:184-187)
+    // is not a pass of its own: the SpMV of iteration k forms it on the fly for every column it gathers
+    // (p_old, r and Minv of the neighbours - all L2 resident at the sizes this kernel serves) with the very
+    // fma the owner uses, and the row's owner stores p_k into the OTHER p buffer for the x update and the next
+    // iteration.  Same values, same summation order as the three-pass loop; one pass and one barrier less.
+    float* pbuf[2] = {a.p, a.p2};
+    int cur = 0;                     // pbuf[cur] holds p_{k-1} (p_0 = z_0 for k = 1, used with beta = 0)
+    float beta = 0.0f;
     for (int k = 1; k <= a.maxiter; ++k) {
         niters = k;
+        const float* pold = pbuf[cur];
+        float* pnew = pbuf[cur ^ 1];
+        const bool first = k == 1;
         // q = A p ; pq = p.q
         float loc_pq = 0.0f;
         for (int row = gid; row < nround; row += ngroups) {
-            {
-                const bool valid = row < a.n;
-                const float ap = row_dot<G>(a.col, a.val, a.p, valid ? a.rowptr[row] : 0,
-                                            valid ? a.rowptr[row + 1] : 0, sub, true);
-                if (valid && sub == 0) {
-                    __stcg(a.q + row, ap);
-                    loc_pq = fmaf(__ldcg(a.p + row), ap, loc_pq);
+            const bool valid = row < a.n;
+            const int beg = valid ? a.rowptr[row] : 0, end = valid ? a.rowptr[row + 1] : 0;
+            float acc = 0.0f;
+            for (int e = beg + sub; e < end; e += G) {
+                const int c = a.col[e];
+                float pj = __ldcg(pold + c);
+                if (!first) {
+                    const float rj = __ldcg(a.r + c);
+                    pj = fmaf(beta, pj, a.minv ? a.minv[c] * rj : rj);
                 }
+                acc = fmaf(a.val[e], pj, acc);
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
+            if (valid && sub == 0) {
+                float pi = __ldcg(pold + row);
+                if (!first) {
+                    const float ri = __ldcg(a.r + row);
+                    pi = fmaf(beta, pi, a.minv ? a.minv[row] * ri : ri);
+                }
+                __stcg(pnew + row, pi);
+                __stcg(a.q + row, acc);
+                loc_pq = fmaf(pi, acc, loc_pq);
             }
         }
         v = block_sum(loc_pq, sh);
@@ -116,7 +143,7 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
         // x += alpha p ; r -= alpha q ; res = r.r ; z = Minv r ; rz' = r.z   (conjgrad.py:172-183)
         loc_rz = 0.0f; loc_rr = 0.0f;
         for (int i = tid; i < a.n; i += nthreads) {
-            const float pi = __ldcg(a.p + i);
+            const float pi = __ldcg(pnew + i);
             __stcg(a.x + i, fmaf(alpha, pi, __ldcg(a.x + i)));
             const float r = fmaf(-alpha, __ldcg(a.q + i), __ldcg(a.r + i));
             __stcg(a.r + i, r);
@@ -126,17 +153,11 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
         }
         v = block_sum(loc_rz, sh);
         w = block_sum(loc_rr, sh);
+        // the partials of the two phases live in different arrays and each array is rewritten two barriers later
         if (threadIdx.x == 0) { __stcg(part_rz + blockIdx.x, v); __stcg(part_rr + blockIdx.x, w); }
         grid.sync();
         const float rznew = grid_total(part_rz, sh);
         res = grid_total(part_rr, sh);
-        const float beta = rznew / rz;
-        // p = z + beta p
-        for (int i = tid; i < a.n; i += nthreads) {
-            const float r = __ldcg(a.r + i);
-            const float z = a.minv ? a.minv[i] * r : r;
-            __stcg(a.p + i, fmaf(beta, __ldcg(a.p + i), z));
-        }
         // batched convergence test + NaN/Inf guard (conjgrad.py:293-300)
         if (k % a.check_every == 0) {
             const bool finite = isfinite(res);
@@ -145,8 +166,9 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
                 break;
             }
         }
+        beta = rznew / rz;
         rz = rznew;
-        grid.sync();
+        cur ^= 1;
     }
     if (niters >= a.maxiter) flags |= 1;
     if (tid == 0 && a.info) {
@@ -334,7 +356,7 @@ int pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const f
         if (e && std::atoi(e) > 0) nb = std::min<long long>(std::atoi(e), (long long)sms * per_sm);
     }
     s->nblocks = (int)nb;
-    if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 3 * (size_t)n), "cudaMalloc(pcg work)")) { delete s; return 1; }
+    if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 4 * (size_t)n), "cudaMalloc(pcg work)")) { delete s; return 1; }
     if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 3 * (size_t)s->nblocks), "cudaMalloc(pcg partials)")) {
         cudaFree(s->work); delete s; return 1;
     }
@@ -369,7 +391,7 @@ static int pcg_launch(pdx_pcg* s, const float* b, const float* mval, const float
     PcgArgs a{};
     a.n = s->n; a.rowptr = s->rowptr; a.col = s->col; a.val = s->val; a.minv = s->minv;
     a.b = b; a.mval = mval; a.rhs0 = rhs0; a.x = x;
-    a.r = s->work; a.p = s->work + s->n; a.q = s->work + 2 * (size_t)s->n;
+    a.r = s->work; a.p = s->work + s->n; a.q = s->work + 2 * (size_t)s->n; a.p2 = s->work + 3 * (size_t)s->n;
     a.part = s->part;
     a.maxiter = maxiter;
     a.check_every = check_every > 0 ? check_every : 1;

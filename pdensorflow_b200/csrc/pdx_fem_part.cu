@@ -78,7 +78,7 @@ struct PartArgs {
     float* p;                        // window
     float* zg;                       // window; only the ghost parts are used
     float *r, *q;                    // n
-    float* part;                     // 2 * gridDim.x
+    float* part;                     // 2 buffers x 2 scalars x gridDim.x
     Comm* comm;
     Comm* peer[MAXW];
     // where this rank's first send_lo / last send_hi rows live in the neighbours' windows
@@ -101,18 +101,28 @@ __device__ __forceinline__ bool all_reduce(const PartArgs& a, cg::grid_group& gr
     const int nb = gridDim.x;
     float v0 = block_sum(loc0, sh);
     float v1 = NV > 1 ? block_sum(loc1, sh) : 0.0f;
+    // the block partials alternate between two buffers: a block may already publish the partial of the NEXT
+    // all-reduce while a slower block is still adding up this one's (they are two grid barriers apart per buffer)
+    float* part = a.part + ((epoch + 1) & 1) * 2 * nb;
     if (threadIdx.x == 0) {
-        __stcg(a.part + blockIdx.x, v0);
-        if (NV > 1) __stcg(a.part + nb + blockIdx.x, v1);
+        __stcg(part + blockIdx.x, v0);
+        if (NV > 1) __stcg(part + nb + blockIdx.x, v1);
     }
     if (pushed) __threadfence_system();   // this thread's peer stores (z of the edge rows) before the publication
     grid.sync();
     ++epoch;
+    if (a.world == 1) {
+        // one rank: nothing to exchange - every block adds the block partials itself, in the same order, so all
+        // blocks hold the same bits; no publication by block 0, no second wait
+        *out0 = grid_total(part, sh);
+        if (NV > 1) *out1 = grid_total(part + nb, sh);
+        return true;
+    }
     const int par = epoch & 1;
     Comm* me = a.comm;
     if (blockIdx.x == 0) {
-        const float t0 = grid_total(a.part, sh);
-        const float t1 = NV > 1 ? grid_total(a.part + nb, sh) : 0.0f;
+        const float t0 = grid_total(part, sh);
+        const float t1 = NV > 1 ? grid_total(part + nb, sh) : 0.0f;
         __shared__ float got[2][MAXW];
         __shared__ int timed_out;
         if (threadIdx.x == 0) timed_out = 0;
@@ -391,7 +401,7 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     s->p    = (float*)(s->ws + COMM_BYTES);
     s->zg   = (float*)(s->ws + COMM_BYTES + vec);
     if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 2 * (size_t)d->n_local), "cudaMalloc(pcg_part work)")) { delete s; return 1; }
-    if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 2 * (size_t)s->nblocks), "cudaMalloc(pcg_part partials)")) {
+    if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 4 * (size_t)s->nblocks), "cudaMalloc(pcg_part partials)")) {
         cudaFree(s->work); delete s; return 1;
     }
     if (check_cuda(cudaMemset(s->ws, 0, COMM_BYTES + 2 * vec), "clear comm block") ||     // comm, p, zg

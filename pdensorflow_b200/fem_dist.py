@@ -80,6 +80,117 @@ def csr_to_sell32(rowptr, col, val, row_lo=0):
     return slice_ptr.astype(np.int32), scol.astype(np.int32), sval
 
 
+def csr_to_sell32_device(rowptr, col, val, row_lo=0):
+    """``csr_to_sell32`` on the device (pdx_sell_slice_widths / pdx_sell_fill): CUDA tensors in (rowptr int32 [n+1],
+    col int32, val fp32), CUDA tensors out (slice_ptr int32, col int32, val fp32), identical to the host conversion.
+    Sits next to the device assembly (gpuSolve.matrices.device_assembly): a mesh assembled on the GPU never visits the
+    host on its way to the SELL kernels."""
+    for t, dt in ((rowptr, torch.int32), (col, torch.int32), (val, torch.float32)):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise L.PdxError('csr_to_sell32_device takes contiguous CUDA tensors (int32 rowptr/col, fp32 val)')
+    n = rowptr.numel() - 1
+    nsl = (n + 31) // 32
+    lib = L.lib()
+    with torch.cuda.device(rowptr.device):
+        widths = torch.empty(max(nsl, 1), dtype=torch.int32, device=rowptr.device)
+        L.check(lib.pdx_sell_slice_widths(n, L.ptr(rowptr), L.ptr(widths), L.stream_ptr()))
+        sp = torch.zeros(nsl + 1, dtype=torch.int64, device=rowptr.device)
+        torch.cumsum(widths[:nsl].to(torch.int64) * 32, 0, out=sp[1:])
+        total = int(sp[-1])                                     # one host read: the size of the SELL arrays
+        if total >= 2 ** 31:
+            raise ValueError('SELL storage exceeds int32 offsets: partition the matrix over more ranks')
+        sp32 = sp.to(torch.int32)
+        scol = torch.empty(total, dtype=torch.int32, device=rowptr.device)
+        sval = torch.empty(total, dtype=torch.float32, device=rowptr.device)
+        L.check(lib.pdx_sell_fill(n, int(row_lo), L.ptr(rowptr), L.ptr(col), L.ptr(val), L.ptr(sp32), L.ptr(scol),
+                                  L.ptr(sval), L.stream_ptr()))
+    return sp32, scol, sval
+
+
+def sell_padding(row_lengths, order=None):
+    """Stored / useful entries of SELL-32 for rows of these lengths (optionally visited in ``order``)."""
+    lens = np.asarray(row_lengths, dtype=np.int64)
+    if order is not None:
+        lens = lens[np.asarray(order)]
+    n = lens.shape[0]
+    pad = np.zeros((n + 31) // 32 * 32, dtype=np.int64)
+    pad[:n] = lens
+    return float(pad.reshape(-1, 32).max(axis=1).sum() * 32) / max(int(lens.sum()), 1)
+
+
+def sigma_window_order(row_lengths, sigma=256, blocks=None):
+    """SELL-C-sigma row order (C = 32): inside windows of ``sigma`` consecutive rows the rows are sorted by decreasing
+    length, so that the 32 rows of a slice have similar lengths and little padding; windows never straddle a
+    partition block (``blocks`` = [(lo, hi)] of the row-block partition), so the ordering is partition aware: the
+    rows a rank owns stay the rows it owns and the band structure moves by less than sigma.
+    Returns ``perm`` (new position -> old row), to be composed with the mesh renumbering like the reference's RCM
+    ``perm`` (gpuSolve/matrices/globalMatrices.py:54-74) - i.e. applied to rows AND columns before assembly /
+    with ``permute_csr``."""
+    lens = np.asarray(row_lengths, dtype=np.int64)
+    n = lens.shape[0]
+    if sigma % 32 or sigma <= 0:
+        raise ValueError('sigma must be a positive multiple of the slice height 32')
+    blocks = [(0, n)] if blocks is None else list(blocks)
+    win = np.empty(n, dtype=np.int64)
+    base = 0
+    for lo, hi in blocks:
+        win[lo:hi] = base + (np.arange(hi - lo) // sigma)
+        base += -(-(hi - lo) // sigma)
+    return np.lexsort((np.arange(n), -lens, win)).astype(np.int64)      # stable: ties keep their order
+
+
+def permute_csr(rowptr, col, val, perm):
+    """P A P^T for the renumbering new -> old ``perm``: row i of the result is old row perm[i] with its columns
+    relabelled through the inverse permutation; the entries of a row keep their order."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    perm = np.asarray(perm, dtype=np.int64)
+    n = perm.shape[0]
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n)
+    lens = np.diff(rowptr)[perm]
+    new_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=new_ptr[1:])
+    src = np.repeat(rowptr[perm], lens) + (np.arange(new_ptr[-1]) - np.repeat(new_ptr[:-1], lens))
+    return new_ptr.astype(np.int32), iperm[np.asarray(col, dtype=np.int64)[src]].astype(np.int32), np.asarray(val)[src]
+
+
+def ghost_columns(col, lo, hi):
+    """Sorted unique global columns a block of rows [lo, hi) touches outside itself."""
+    c = np.asarray(col, dtype=np.int64)
+    return np.unique(c[(c < lo) | (c >= hi)])
+
+
+def plan_ghost_lists(blocks, ghosts):
+    """General ghost exchange of a row-block partition (no band assumption).
+
+    blocks: [(lo, hi)] per rank; ghosts: per rank the sorted global columns it needs from other ranks
+    (``ghost_columns``).  Returns per rank a pair (rows, peers): after each step rank r stores row rows[k] of its
+    new potential into rank peers[k]'s buffer (pdx_push_rows)."""
+    world = len(blocks)
+    bounds = np.array([b[0] for b in blocks] + [blocks[-1][1]], dtype=np.int64)
+    send = [([], []) for _ in range(world)]
+    for r, g in enumerate(ghosts):
+        g = np.asarray(g, dtype=np.int64)
+        if g.size == 0:
+            continue
+        if g.min() < bounds[0] or g.max() >= bounds[-1]:
+            raise ValueError('rank %d needs columns outside the matrix' % r)
+        owner = np.searchsorted(bounds, g, side='right') - 1
+        for o in np.unique(owner):
+            if o == r:
+                raise ValueError('rank %d lists one of its own rows as a ghost' % r)
+            rows = g[owner == o]
+            send[o][0].append(rows)
+            send[o][1].append(np.full(rows.shape[0], r, dtype=np.int64))
+    out = []
+    for rows, peers in send:
+        if rows:
+            out.append((np.concatenate(rows).astype(np.int32), np.concatenate(peers).astype(np.int32)))
+        else:
+            out.append((np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32)))
+    return out
+
+
 class PartitionedExplicitFEM:
     """One rank's block of the explicit lumped monodomain step.
 
@@ -89,7 +200,7 @@ class PartitionedExplicitFEM:
     """
 
     def __init__(self, n_global, rowptr, col, kval, mlump, dt, model='fenton4v', params=None, rank=0, world=1,
-                 group=None, math='fast', device=None, layout='sell', connect=True):
+                 group=None, math='fast', device=None, layout='sell', connect=True, exchange='auto'):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != 'cuda':
             raise L.PdxError('PartitionedExplicitFEM needs a CUDA device: there is no CPU path')
@@ -102,7 +213,14 @@ class PartitionedExplicitFEM:
         if rowptr.shape[0] != self.nloc + 1:
             raise ValueError('rowptr must describe the %d rows of this rank' % self.nloc)
         self.col_range = (int(col.min()), int(col.max()))
+        self.ghosts = ghost_columns(col, self.lo, self.hi)
         self.send_lo = self.send_hi = 0
+        # exchange: 'band' = the neighbours' edge rows, stored by the step kernel itself (banded orderings);
+        # 'lists' = index lists + pdx_push_rows (any partition); 'auto' = band when the partition allows it
+        if exchange not in ('auto', 'band', 'lists'):
+            raise ValueError("exchange must be 'auto', 'band' or 'lists'")
+        self.exchange = exchange
+        self._push = None
         self._local = world > 1 and not connect      # ranks sharing one GPU in one process: see connect_local
         if world > 1 and connect:
             import torch.distributed as dist
@@ -110,19 +228,18 @@ class PartitionedExplicitFEM:
             allr = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine, group=group)
             ranges = [tuple(int(v) for v in t.tolist()) for t in allr]
-            self.send_lo, self.send_hi = plan_exchange(self.blocks, ranges, rank)
+            self._plan(ranges, lambda: self._gather_ghosts(group))
         dev = self.device
         self.layout = layout
         self.nnz = int(rowptr[-1])
-        if layout == 'sell':
-            sp, scol, sval = csr_to_sell32(rowptr, col, kval, self.lo)
-            self.padding = scol.shape[0] / max(self.nnz, 1)
-            rowptr, col, kval = sp, scol, sval
-        elif layout != 'csr':
+        if layout not in ('sell', 'csr'):
             raise ValueError("layout must be 'sell' or 'csr'")
         self.rowptr = torch.from_numpy(rowptr).to(dev)
         self.col = torch.from_numpy(col).to(dev)
         self.kval = torch.from_numpy(np.ascontiguousarray(kval, dtype=np.float32)).to(dev)
+        if layout == 'sell':       # CSR -> SELL-32 on the device (pdx_sell_fill); the CSR copy is dropped
+            self.rowptr, self.col, self.kval = csr_to_sell32_device(self.rowptr, self.col, self.kval, self.lo)
+            self.padding = self.col.numel() / max(self.nnz, 1)
         if layout == 'csr':
             L.check(L.lib().pdx_csr_hint(L.ptr(self.rowptr), self.nloc, self.nnz))     # lanes per row of the CSR kernel
         self.mlinv = torch.from_numpy((1.0 / np.asarray(mlump, dtype=np.float64)).astype(np.float32)).to(dev)
@@ -146,9 +263,39 @@ class PartitionedExplicitFEM:
             self._peer_lo = self._peer_hi = [None, None]
         for b in self.U:
             b.fill_(-80.0 if self.model_id != L.MODEL_NONE else 0.0)
+        if self._hdl is not None and self.exchange == 'lists':
+            self._install_push([[int(q) for q in h.buffer_ptrs] for h in self._hdl])
         self._cur = 0
         self._primed = world == 1 or self._local
         self.nsteps_done = 0
+
+    # ---- exchange planning --------------------------------------------------------------------
+    def _gather_ghosts(self, group):
+        import torch.distributed as dist
+        allg = [None] * self.world
+        dist.all_gather_object(allg, self.ghosts, group=group)
+        return allg
+
+    def _plan(self, ranges, all_ghosts):
+        """Band exchange when every rank's ghosts sit in its two neighbours, index lists otherwise."""
+        if self.exchange in ('auto', 'band'):
+            try:
+                self.send_lo, self.send_hi = plan_exchange(self.blocks, ranges, self.rank)
+                self.exchange = 'band'
+                return
+            except ValueError:
+                if self.exchange == 'band':
+                    raise
+        self.exchange = 'lists'
+        self.send_lo = self.send_hi = 0
+        self._push_plan = plan_ghost_lists(self.blocks, all_ghosts())[self.rank]
+
+    def _install_push(self, peer_ptrs):
+        """peer_ptrs[b][r] = device address of rank r's U buffer b."""
+        rows, peers = self._push_plan
+        dev = self.device
+        self._push = (torch.from_numpy(rows).to(dev), torch.from_numpy(peers).to(dev),
+                      [torch.tensor(p, dtype=torch.int64, device=dev) for p in peer_ptrs], int(rows.shape[0]))
 
     @staticmethod
     def connect_local(ranks):
@@ -157,10 +304,14 @@ class PartitionedExplicitFEM:
         the step kernel are exercised on a single-GPU box.  Step the ranks with ``step_local``."""
         ranks = sorted(ranks, key=lambda f: f.rank)
         ranges = [f.col_range for f in ranks]
+        ghosts = [f.ghosts for f in ranks]
         for f in ranks:
-            f.send_lo, f.send_hi = plan_exchange(f.blocks, ranges, f.rank)
+            f._plan(ranges, lambda: ghosts)
             f._peer_lo = [ranks[f.rank - 1].U[b].data_ptr() if f.rank > 0 else None for b in range(2)]
             f._peer_hi = [ranks[f.rank + 1].U[b].data_ptr() if f.rank < f.world - 1 else None for b in range(2)]
+            if f.exchange == 'lists':
+                f._peer_lo = f._peer_hi = [None, None]
+                f._install_push([[g.U[b].data_ptr() for g in ranks] for b in range(2)])
 
     @staticmethod
     def step_local(ranks, nsteps=1):
@@ -199,6 +350,10 @@ class PartitionedExplicitFEM:
                 L.ptr(self.kval), L.ptr(self.mlinv), L.ptr(self.U[i]), L.ptr(self.U[o]), self._states_arr, L.ptr(I0),
                 dt32, self.send_lo, C.c_void_p(self._peer_lo[o]), self.send_hi, C.c_void_p(self._peer_hi[o]),
                 L.stream_ptr()))
+            if self._push is not None and self._push[3]:      # general partitions: rows other ranks hold as ghosts
+                rows, peers, bufs, count = self._push
+                L.check(lib.pdx_push_rows(L.ptr(self.U[o]), count, L.ptr(rows), L.ptr(peers), L.ptr(bufs[o]),
+                                          L.stream_ptr()))
             if self.world > 1 and not self._local:
                 self._hdl[0].barrier(channel=0)
             self._cur = o
@@ -342,15 +497,16 @@ class PartitionedSemiImplicitFEM:
         dev = self.device
         rowptr, col = self._rowptr_h, (self._col_h - (self.lo - self.glo)).astype(np.int32)   # window-local columns
         aval, mval = self._aval_h, self._mval_h
-        if self.layout == 'sell':       # SELL-32: thread per row, coalesced matrix loads (as the explicit step)
-            sp, scol, aval = csr_to_sell32(rowptr, col, aval, self.glo)
-            _, _, mval = csr_to_sell32(rowptr, col, mval, self.glo)
-            self.padding = scol.shape[0] / max(int(rowptr[-1]), 1)
-            rowptr, col = sp, scol
         self.rowptr = torch.from_numpy(rowptr).to(dev)
         self.col = torch.from_numpy(col).to(dev)
         self.aval = torch.from_numpy(np.ascontiguousarray(aval)).to(dev)
         self.mval = torch.from_numpy(np.ascontiguousarray(mval)).to(dev)
+        if self.layout == 'sell':       # SELL-32: thread per row, coalesced matrix loads (as the explicit step), built on the device
+            nnz = int(rowptr[-1])
+            sp, scol, self.aval = csr_to_sell32_device(self.rowptr, self.col, self.aval, self.glo)
+            _, _, self.mval = csr_to_sell32_device(self.rowptr, self.col, self.mval, self.glo)
+            self.rowptr, self.col = sp, scol
+            self.padding = scol.numel() / max(nnz, 1)
         self.minv = torch.from_numpy(self._minv_h).to(dev)
         d = L.PcgPartDesc()
         d.n_local, d.ghost_lo, d.ghost_hi = self.nloc, self.glo, self.ghi

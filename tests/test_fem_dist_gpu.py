@@ -134,3 +134,70 @@ def test_ranks_sharing_one_gpu_match_single_rank_bitwise(cuda, world, layout):
     for f in ranks:
         assert np.array_equal(f.owned_U().cpu().numpy(), Uref[f.lo:f.hi])
         assert np.array_equal(f.states[0].cpu().numpy(), Vref[f.lo:f.hi])
+
+
+# ------------------------------------------------------------------------------ N3: unstructured meshes
+def _unstructured_operator(npts=2500, seed=6):
+    """Stiffness + lumped mass of a Delaunay tetrahedral mesh in RCM order, conductivity scaled so that the explicit
+    step is stable (dt * Gershgorin bound = 0.5)."""
+    from oracle import fem as ofem
+    from test_fem_partition_cpu import unstructured_tet_mesh
+    P, E, F = unstructured_tet_mesh(npts, seed)
+    n = P.shape[0]
+    ren = ofem.rcm_indexing(ofem.coo_pattern(ofem.connectivity(n, E)))
+    m = ofem.assemble(P, E, F, {1: 1.0}, {1: 1.0}, ren['iperm'])
+    rp, ci = m['rowptr'], m['col']
+    ml = np.add.reduceat(m['mass'].astype(np.float64), rp[:-1])
+    bound = (np.add.reduceat(np.abs(m['stiffness']).astype(np.float64), rp[:-1]) / ml).max()
+    kv = (m['stiffness'] * np.float32(0.5 / (DT * bound))).astype(np.float32)
+    U0 = np.where(P[ren['perm'], 0] < 0.2, 20.0, -80.0).astype(np.float32)
+    return n, rp, ci, kv, ml.astype(np.float32), U0
+
+
+def test_device_sell_conversion_equals_host_conversion(cuda):
+    from pdensorflow_b200.fem_dist import csr_to_sell32, csr_to_sell32_device
+    n, rp, ci, kv, ml, _ = _unstructured_operator(1100)
+    for lo, hi in ((0, n), (137, 1001), (500, 532), (40, 41)):
+        rpl = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+        cl, vl = ci[rp[lo]:rp[hi]], kv[rp[lo]:rp[hi]]
+        sp, sc, sv = csr_to_sell32(rpl, cl, vl, lo)
+        dsp, dsc, dsv = csr_to_sell32_device(torch.from_numpy(rpl).cuda(), torch.from_numpy(cl.astype(np.int32)).cuda(),
+                                             torch.from_numpy(vl).cuda(), lo)
+        assert np.array_equal(dsp.cpu().numpy(), sp) and np.array_equal(dsc.cpu().numpy(), sc)
+        assert np.array_equal(dsv.cpu().numpy(), sv)
+
+
+@pytest.mark.parametrize('world,layout', [(11, 'sell'), (6, 'csr')])
+def test_general_ghost_lists_on_an_unstructured_mesh_bitwise(cuda, world, layout):
+    """Row blocks of an unstructured (Delaunay) tetrahedral mesh: the RCM band is wider than a block, so ghosts reach
+    past the two neighbours and travel through index lists + pdx_push_rows.  Ranks share one GPU (plain device pointers,
+    one stream); every rank's rows must equal the single-rank run bitwise."""
+    from pdensorflow_b200.fem_dist import PartitionedExplicitFEM, row_blocks
+    n, rp, ci, kv, ml, U0 = _unstructured_operator()
+    nsteps = 30
+    ranks = []
+    for r, (lo, hi) in enumerate(row_blocks(n, world)):
+        sl = slice(rp[lo], rp[hi])
+        ranks.append(PartitionedExplicitFEM(n, rp[lo:hi + 1] - rp[lo], ci[sl], kv[sl], ml[lo:hi], DT, model='fenton4v',
+                                            math='exact', rank=r, world=world, layout=layout, connect=False))
+    PartitionedExplicitFEM.connect_local(ranks)
+    assert all(f.exchange == 'lists' for f in ranks)
+    assert max(len(set(f._push[1].cpu().tolist())) for f in ranks) > 2          # some rank feeds more than two others
+    for f in ranks:
+        f.set_global_U(U0)
+    PartitionedExplicitFEM.step_local(ranks, nsteps)
+    torch.cuda.synchronize()
+    ref = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', layout=layout)
+    ref.set_global_U(U0)
+    ref.step(nsteps)
+    Uref, Vref = ref.current_U().cpu().numpy(), ref.states[0].cpu().numpy()
+    assert np.isfinite(Uref).all() and np.unique(Uref).shape[0] > n // 2        # diffusion did couple the nodes
+    for f in ranks:
+        assert np.array_equal(f.owned_U().cpu().numpy(), Uref[f.lo:f.hi]), f.rank
+        assert np.array_equal(f.states[0].cpu().numpy(), Vref[f.lo:f.hi])
+    # forcing the band plan on this partition is refused
+    with pytest.raises(ValueError):
+        bad = [PartitionedExplicitFEM(n, rp[lo:hi + 1] - rp[lo], ci[rp[lo]:rp[hi]], kv[rp[lo]:rp[hi]], ml[lo:hi], DT,
+                                      rank=r, world=world, layout=layout, connect=False, exchange='band')
+               for r, (lo, hi) in enumerate(row_blocks(n, world))]
+        PartitionedExplicitFEM.connect_local(bad)
