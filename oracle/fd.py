@@ -2,8 +2,10 @@
 
 TEST INFRASTRUCTURE - see ``oracle/__init__.py``.  Not imported by the product.
 NumPy fp32, op-for-op in the order the reference source writes the expressions.
-PARITY UNPINNED by reference golden vectors (the reference has no test for these
-operators); frozen into ``tests/golden/`` instead.
+PINNED: the reference ships no golden vectors for these operators, so its own source is executed over a NumPy
+TensorFlow facade (tests/golden/make_ref_golden.py, make_heat_golden.py, make_atria_golden.py) and the outputs are
+frozen in tests/golden/ref_fd.npz / ref_heat.npz / ref_atria.npz; tests/test_ref_golden_cpu.py and
+tests/test_atria_cpu.py check that this restatement reproduces them bit for bit.
 """
 import numpy as np
 
