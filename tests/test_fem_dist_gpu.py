@@ -150,7 +150,8 @@ def _unstructured_operator(npts=2500, seed=6):
     ml = np.add.reduceat(m['mass'].astype(np.float64), rp[:-1])
     bound = (np.add.reduceat(np.abs(m['stiffness']).astype(np.float64), rp[:-1]) / ml).max()
     kv = (m['stiffness'] * np.float32(0.5 / (DT * bound))).astype(np.float32)
-    U0 = np.where(P[ren['perm'], 0] < 0.2, 20.0, -80.0).astype(np.float32)
+    # S1 region + a rough sub-threshold field everywhere, so that every row's K.U term matters in the bits
+    U0 = np.where(P[ren['perm'], 0] < 0.2, 20.0, -80.0 + 25.0 * np.random.default_rng(seed).uniform(size=n)).astype(np.float32)
     return n, rp, ci, kv, ml.astype(np.float32), U0
 
 
@@ -191,7 +192,7 @@ def test_general_ghost_lists_on_an_unstructured_mesh_bitwise(cuda, world, layout
     ref.set_global_U(U0)
     ref.step(nsteps)
     Uref, Vref = ref.current_U().cpu().numpy(), ref.states[0].cpu().numpy()
-    assert np.isfinite(Uref).all() and np.unique(Uref).shape[0] > n // 2        # diffusion did couple the nodes
+    assert np.isfinite(Uref).all() and np.unique(Uref).shape[0] > 0.9 * n
     for f in ranks:
         assert np.array_equal(f.owned_U().cpu().numpy(), Uref[f.lo:f.hi]), f.rank
         assert np.array_equal(f.states[0].cpu().numpy(), Vref[f.lo:f.hi])
