@@ -446,8 +446,9 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
             std::swap(a.rhxsq, a.rhzsq);
         }
         const CUtensorMap* mS[PDX_MAX_STATES] = {nullptr, nullptr, nullptr, nullptr};
-        // 2-D fields give each CTA a single plane: nothing to pipeline, the register path is faster
-        const bool use_tst = p->tma_states && ns > 0 && a.has_x;
+        // 3-D: planes of the x-march; 2-D: the y-tiles a CTA marches over (x_chunk > 1) - a single tile per CTA has
+        // nothing to pipeline and keeps the register path
+        const bool use_tst = p->tma_states && ns > 0 && (a.has_x || a.x_chunk > 1);
         if (use_tst)
             for (int i = 0; i < ns; ++i)
                 if (get_state_map(p, states[i], &mS[i])) return 1;

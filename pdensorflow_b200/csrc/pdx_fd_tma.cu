@@ -140,29 +140,37 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
         const int t = g0 + (r - chunk * gsz);
         tz = t % a.ntz;
         ty = t / a.ntz;
-    } else {
+    } else if (HAS_X) {
         tz = b % a.ntz;  b /= a.ntz;
         ty = b % a.nty;  b /= a.nty;
         chunk = b;
+    } else {
+        // 2-D fields: a CTA marches over x_chunk consecutive y-tiles of one z-strip, so that the TMA rings have
+        // something to pipeline (a tile per CTA is launch-and-wait: 0.70 of the HBM peak on 4096^2)
+        tz = b % a.ntz;
+        ty = (b / a.ntz) * a.x_chunk;
+        chunk = 0;
     }
-    const int z0 = tz * TZ, y0 = ty * TY;
-    const int xb = a.xb + chunk * a.x_chunk;
-    const int xe = min(xb + a.x_chunk, a.xe);
-    const int np = xe - xb;
+    const int z0 = tz * TZ;
+    const int y00 = ty * TY;                        // first (2-D: marched) y-tile of the CTA
+    const int xb = HAS_X ? a.xb + chunk * a.x_chunk : a.xb;
+    const int xe = HAS_X ? min(xb + a.x_chunk, a.xe) : a.xe;
+    const int np = HAS_X ? xe - xb : min(a.x_chunk, a.nty - ty);    // march steps: planes (3-D) or y-tiles (2-D)
     const int nlog = HAS_X ? np + 2 : np;           // logical planes q = xb-1 .. xe (3-D)
     const bool down = HAS_X && a.raster > 0 && (chunk & 1);   // CTA uniform
     const int qs = down ? -1 : 1;                   // logical plane j is array plane q0 + qs*j
     const int q0 = HAS_X ? (down ? xe : xb - 1) : xb;
     const int p0 = down ? xe - 1 : xb;              // i-th plane advanced: p0 + qs*i
+    auto y0_of = [&](int i) { return HAS_X ? y00 : y00 + i * TY; };   // y origin of march step i
 
     auto slotU = [&](int j) { return reinterpret_cast<float*>(smem + (j % NSTAGE) * G::SLOT_BYTES); };
     auto slotD = [&](int j) { return reinterpret_cast<float*>(smem + (j % NSTAGE) * G::SLOT_BYTES + G::FIELD_BYTES); };
     auto issue = [&](int j) {   // thread 0 only
-        const int q = q0 + qs * j;
+        const int q = q0 + qs * j;                  // 3-D only
         uint64_t* bar = &full[j % NSTAGE];
         mbar_expect_tx(bar, G::TX_BYTES);
-        tma_load_3d(slotU(j), &mapU, z0 - ZH, y0 - 1, HAS_X ? clampi(q, a.xclo, a.xchi) : q, bar);
-        if (HET) tma_load_3d(slotD(j), &mapD, z0 - ZH, y0 - 1, HAS_X ? clampi(q, a.dxlo, a.dxhi) : q, bar);
+        tma_load_3d(slotU(j), &mapU, z0 - ZH, y0_of(j) - 1, HAS_X ? clampi(q, a.xclo, a.xchi) : xb, bar);
+        if (HET) tma_load_3d(slotD(j), &mapD, z0 - ZH, y0_of(j) - 1, HAS_X ? clampi(q, a.dxlo, a.dxhi) : xb, bar);
     };
     auto wait_plane = [&](int j) { mbar_wait(&full[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1)); };
     auto sslot = [&](int i, int s) {
@@ -172,7 +180,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
         uint64_t* bar = &sfull[i % SSTAGES];
         mbar_expect_tx(bar, NS * G::ST_BYTES);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) tma_load_3d(sslot(i, s), &mapS.m[s], z0, y0, p0 + qs * i, bar);
+        for (int s = 0; s < NS; ++s) tma_load_3d(sslot(i, s), &mapS.m[s], z0, y0_of(i), HAS_X ? p0 + qs * i : xb, bar);
     };
 
     if (tid == 0) {
@@ -196,25 +204,29 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
     const int  col  = ZH + 4 * lane;
     const bool zact = z < a.nz;
     const bool zb_tile = (z0 - 1 < a.zclo) || (z0 + TZ > a.zchi);            // CTA uniform
-    const bool yb_tile = (y0 - 1 < a.yclo) || (y0 + TY > a.ychi);            // CTA uniform
     const bool lo2 = z < a.zclo, lo1 = z - 1 < a.zclo;
     const bool hi2 = z + 3 > a.zchi, hi1 = z + 4 > a.zchi;
     const bool dlo1 = z - 1 < 0, dhi1 = z + 4 > a.nz - 1;                    // DIFF: symmetric pad only
 
-    int  gy[R], rc[R], rm[R], rp[R], drm[R], drp[R];
-    bool act[R];
+    // row geometry of a y-tile: constant along the march in 3-D, recomputed per marched tile in 2-D
+    int  gy[R], rc[R], rm[R], rp[R], drm[R], drp[R], drc0;
+    bool act[R], yb_tile;
+    auto row_geometry = [&](int y0) {
+        yb_tile = (y0 - 1 < a.yclo) || (y0 + TY > a.ychi);                   // CTA uniform
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        gy[r]  = y0 + warp * R + r;
-        act[r] = zact && gy[r] < a.ny;
-        const int g = min(gy[r], a.ny - 1);          // keep inactive rows addressable
-        rc[r]  = (clampi(g, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
-        rm[r]  = (clampi(g - 1, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
-        rp[r]  = (clampi(g + 1, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
-        drm[r] = (max(g - 1, 0) - (y0 - 1)) * COLS + col;
-        drp[r] = (min(g + 1, a.ny - 1) - (y0 - 1)) * COLS + col;
-    }
-    const int drc0 = (0 - (y0 - 1)) * COLS + col;    // + g*COLS gives the unclamped DIFF row
+        for (int r = 0; r < R; ++r) {
+            gy[r]  = y0 + warp * R + r;
+            act[r] = zact && gy[r] < a.ny;
+            const int g = min(gy[r], a.ny - 1);          // keep inactive rows addressable
+            rc[r]  = (clampi(g, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
+            rm[r]  = (clampi(g - 1, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
+            rp[r]  = (clampi(g + 1, a.yclo, a.ychi) - (y0 - 1)) * COLS + col;
+            drm[r] = (max(g - 1, 0) - (y0 - 1)) * COLS + col;
+            drp[r] = (min(g + 1, a.ny - 1) - (y0 - 1)) * COLS + col;
+        }
+        drc0 = (0 - (y0 - 1)) * COLS + col;              // + g*COLS gives the unclamped DIFF row
+    };
+    row_geometry(y00);
 
     // ---- state prefetch registers ----
     F4 stn[R][NS > 0 ? NS : 1];
@@ -233,8 +245,9 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
     for (int r = 0; r < R; ++r) srow[r] = (warp * R + r) * TZ + 4 * lane;
 
     for (int i = 0; i < np; ++i) {
-        const int p = p0 + qs * i;
+        const int p = HAS_X ? p0 + qs * i : xb;
         const int jc = HAS_X ? i + 1 : i;
+        if (!HAS_X && i > 0) row_geometry(y0_of(i));        // 2-D: the next y-tile of the strip
         if (HAS_X) {
             if (i == 0) { wait_plane(0); wait_plane(1); }
             wait_plane(i + 2);
@@ -260,7 +273,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int s = 0; s < NS; ++s) stc[r][s] = stn[r][s];
-            if (NS > 0 && i + 1 < np) load_states(p + qs);
+            if (HAS_X && NS > 0 && i + 1 < np) load_states(p + qs);   // (2-D marches stage their states by TMA)
         }
 
 #pragma unroll
@@ -360,9 +373,17 @@ int launch_inst(const FdArgs& a0, const CUtensorMap& mU, const CUtensorMap& mD, 
     const int nplanes = a0.xe - a0.xb;
     if (nplanes <= 0) return 0;
     FdArgs a = a0;
-    a.nchunk = (nplanes + a.x_chunk - 1) / a.x_chunk;
-    if (!HAS_X || a.nchunk < 2) a.raster = 0;
-    const long long nb = (long long)a.ntz * a.nty * a.nchunk;
+    if (HAS_X) {
+        a.nchunk = (nplanes + a.x_chunk - 1) / a.x_chunk;
+        if (a.nchunk < 2) a.raster = 0;
+    } else {
+        // 2-D: x_chunk = y-tiles marched per CTA; without TMA-staged states there is nothing to look ahead with
+        if (!TST && NStates<MODEL>::value > 0) a.x_chunk = 1;
+        if (a.x_chunk < 1) a.x_chunk = 1;
+        a.nchunk = (a.nty + a.x_chunk - 1) / a.x_chunk;
+        a.raster = 0;
+    }
+    const long long nb = HAS_X ? (long long)a.ntz * a.nty * a.nchunk : (long long)a.ntz * a.nchunk;
     if (nb > 0x7fffffffLL) { set_error("fd_tma: grid too large"); return 1; }
     kern<<<(unsigned)nb, NTHREADS, G::SMEM_BYTES, s>>>(mU, mD, mS, a);
     count_launch();
@@ -423,7 +444,13 @@ int fd_tma_auto_chunk(const pdx_fd_desc& d) {
     // so the two halo planes each chunk re-reads are L2 hits, and the grid has thousands of CTAs to
     // balance over 148 SMs x 3.  Small grids shorten the chunk further to keep >= 2 waves of CTAs.
     const int nplanes = d.x_end - d.x_begin;
-    if (d.ndim == 2 || nplanes <= 1) return 1;
+    if (d.ndim == 2) {          // y-tiles marched per CTA: as long as the grid still fills the SMs twice over
+        const long long nty = (d.ny + NWARP - 1) / NWARP, ntz = (d.nz + TZ - 1) / TZ;
+        int chunk = 8;
+        while (chunk > 1 && ntz * ((nty + chunk - 1) / chunk) < 148LL * 3 * 2) --chunk;
+        return chunk;
+    }
+    if (nplanes <= 1) return 1;
     const long long tiles = (long long)((d.ny + NWARP - 1) / NWARP) * ((d.nz + TZ - 1) / TZ);
     int chunk = 8;
     while (chunk > 3 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * 3 * 2) --chunk;

@@ -395,3 +395,24 @@ def test_raw_pointer_arguments_are_checked(cuda):
         with pytest.raises(L.PdxError):
             st.apply_stimulus(bad, 60.0)
     assert float(st.U().min()) == 60.0
+
+
+@pytest.mark.parametrize('model', ['fenton4v', 'mms2v', None])
+@pytest.mark.parametrize('shape', [(70, 132), (8, 256), (200, 128), (33, 520)])
+def test_2d_y_march_is_invisible(cuda, model, shape):
+    """2-D grids on the TMA kernel: a CTA marches over x_chunk y-tiles of one z-strip (states staged by TMA).  Every
+    chunk length, incl. ragged last chunks and tiles that touch the y boundary mid-march, must give the bits of the
+    generic kernel; the heterogeneous operator too."""
+    from pdensorflow_b200.fd import FDStepper
+    U, states = random_fields(shape, seed=43, nstates=NSTATES[model])
+    D2 = np.random.default_rng(3).uniform(0.2, 1.0, size=shape).astype(np.float32)
+    for lap, DIFFa in (('homog', None), ('heterog', D2)):
+        ref = FDStepper(shape, (1.0, 0.9), 0.05, 0.8, model=model, math='exact', kernel='generic', lap=lap, DIFF=DIFFa)
+        ref.set_U(U); ref.set_states(states); ref.step(3)
+        for chunk in (0, 1, 2, 3, 8):
+            st = FDStepper(shape, (1.0, 0.9), 0.05, 0.8, model=model, math='exact', kernel='tma', x_chunk=chunk, lap=lap,
+                           DIFF=DIFFa)
+            st.set_U(U); st.set_states(states); st.step(3)
+            assert torch.equal(st.U(), ref.U()), (lap, chunk)
+            for a, b in zip(st.states, ref.states):
+                assert torch.equal(a, b), (lap, chunk)

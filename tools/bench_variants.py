@@ -59,6 +59,13 @@ if __name__ == '__main__':
             for mm in ('fast', 'exact'):
                 bench((256, 256, 256), model=m, nsteps=10, math=mm)
         sys.exit(0)
+    if '--2d' in sys.argv:             # 2-D grids on the per-step TMA kernel (y-march) and the generic kernel
+        for n2 in (4096, 2048, 1024):
+            bench((n2, n2), nsteps=200, kernel='tma')
+        bench((4096, 4096), nsteps=100, kernel='tma', lap='heterog')
+        bench((4096, 4096), nsteps=100, kernel='tma', model='mms2v')
+        bench((4096, 4096), nsteps=100, kernel='generic')
+        sys.exit(0)
     bench(S)
     bench(S, math='exact')
     bench(S, kernel='generic')
