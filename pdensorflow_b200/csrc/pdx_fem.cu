@@ -179,6 +179,175 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
     }
 }
 
+// ---------------------------------------------------------------- PCG, register-resident (small systems)
+// Config 1 (63 001 rows, 4.4e5 non-zeros) is 5 MB: everything sits in L2 and an iteration of pcg_kernel is a chain
+// of dependent L2 round trips (rowptr -> col/val -> gather -> reduce, then the vector passes) between grid barriers.
+// Here every lane group keeps ITS rows for the whole solve: the matrix entries (col, val, Minv of the column) and the
+// row's x, r, Minv, p live in REGISTERS; an iteration is
+//   phase A: gather p_old and z = Minv r of the columns (independent loads, one L2 round trip), form p_k on the fly,
+//            q = A p_k, publish p_k of the own row, p.q partial             -> grid barrier
+//   phase B: x, r of the own rows updated in registers, z published, r.r / r.z partials  -> grid barrier
+// i.e. two barriers and ~one L2 round trip of latency per iteration; x is written once, at the end.  Rows are dealt out
+// exactly as in pcg_kernel (row = group + k * #groups), entries of a row to the lanes in the same order, so every sum
+// has the same order and the iterates are bitwise those of pcg_kernel with the same grid.
+// Needs at most K rows per group and rows of at most E*G entries (checked by the host at pdx_pcg_create).
+template <int G, int K, int E>
+__global__ void __launch_bounds__(256, 4) pcg_small_kernel(const __grid_constant__ PcgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float sh[33];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const int gid = tid / G, sub = threadIdx.x % G, ngroups = nthreads / G;
+    const int nb = gridDim.x;
+    float* part_pq = a.part;
+    float* part_rr = a.part + nb;
+    float* part_rz = a.part + 2 * nb;
+
+    int   ec[K][E];          // column of my e-th entry of my k-th row
+    float ev[K][E];          // its value (0 where the row is shorter)
+    float xk[K], rk[K], mk[K], pk[K], qk[K];
+    bool  own[K];            // this lane owns row k (lane 0 of the group, row < n)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int row = gid + k * ngroups;
+        const bool valid = row < a.n;
+        const int beg = valid ? a.rowptr[row] : 0, end = valid ? a.rowptr[row + 1] : 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int idx = beg + sub + e * G;
+            const bool has = idx < end;
+            ec[k][e] = has ? a.col[idx] : 0;
+            ev[k][e] = has ? a.val[idx] : 0.0f;
+        }
+        own[k] = valid && sub == 0;
+        xk[k] = own[k] ? a.x[row] : 0.0f;
+        mk[k] = (own[k] && a.minv) ? a.minv[row] : 1.0f;
+        rk[k] = pk[k] = qk[k] = 0.0f;
+    }
+
+    // r = b - A x ; z = Minv r ; p = z ; rz = r.z          (conjgrad.py:191-203)
+    float loc_rz = 0.0f, loc_rr = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int row = gid + k * ngroups;
+        const bool valid = row < a.n;
+        float ax = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) ax = fmaf(ev[k][e], a.x[ec[k][e]], ax);     // padded entries add +0
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) ax += __shfl_xor_sync(0xffffffffu, ax, o, G);
+        float bv = 0.0f;
+        if (!a.b) bv = row_dot<G>(a.col, a.mval, a.rhs0, valid ? a.rowptr[row] : 0, valid ? a.rowptr[row + 1] : 0, sub, true);
+        if (own[k]) {
+            if (a.b) bv = a.b[row];
+            const float r = __fsub_rn(bv, ax);
+            const float z = a.minv ? __fmul_rn(mk[k], r) : r;
+            rk[k] = r;
+            pk[k] = z;
+            __stcg(a.p + row, z);
+            loc_rz = fmaf(r, z, loc_rz);
+            loc_rr = fmaf(r, r, loc_rr);
+        }
+    }
+    float v = block_sum(loc_rz, sh);
+    float w = block_sum(loc_rr, sh);
+    if (threadIdx.x == 0) { __stcg(part_rz + blockIdx.x, v); __stcg(part_rr + blockIdx.x, w); }
+    grid.sync();
+    float rz = grid_total(part_rz, sh);
+    float res = grid_total(part_rr, sh);
+
+    int niters = 0, flags = 0, cur = 0;
+    float* pbuf[2] = {a.p, a.p2};
+    float beta = 0.0f;
+    for (int it = 1; it <= a.maxiter; ++it) {
+        niters = it;
+        const float* pold = pbuf[cur];
+        float* pnew = pbuf[cur ^ 1];
+        const bool first = it == 1;
+        // ---- phase A: all gathers of all my rows first (independent loads), then the arithmetic
+        float gp[K][E], gr[K][E];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                gp[k][e] = __ldcg(pold + ec[k][e]);
+                gr[k][e] = first ? 0.0f : __ldcg(a.r + ec[k][e]);       // z = Minv r of the column, published by its owner
+            }
+        float loc_pq = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                float pj = gp[k][e];
+                if (!first) pj = fmaf(beta, pj, gr[k][e]);
+                acc = fmaf(ev[k][e], pj, acc);
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
+            if (own[k]) {
+                if (!first) pk[k] = fmaf(beta, pk[k], a.minv ? mk[k] * rk[k] : rk[k]);
+                __stcg(pnew + gid + k * ngroups, pk[k]);
+                qk[k] = acc;
+                loc_pq = fmaf(pk[k], acc, loc_pq);
+            }
+        }
+        v = block_sum(loc_pq, sh);
+        if (threadIdx.x == 0) __stcg(part_pq + blockIdx.x, v);
+        grid.sync();
+        const float pq = grid_total(part_pq, sh);
+        const float alpha = rz / pq;
+        // ---- phase B: x += alpha p ; r -= alpha q ; res = r.r ; z = Minv r ; rz' = r.z, in registers
+        loc_rz = 0.0f; loc_rr = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (own[k]) {
+                xk[k] = fmaf(alpha, pk[k], xk[k]);
+                const float r = fmaf(-alpha, qk[k], rk[k]);
+                rk[k] = r;
+                const float z = a.minv ? mk[k] * r : r;
+                __stcg(a.r + gid + k * ngroups, z);                 // the work vector "r" carries z for the gathers
+                loc_rr = fmaf(r, r, loc_rr);
+                loc_rz = fmaf(r, z, loc_rz);
+            }
+        }
+        v = block_sum(loc_rz, sh);
+        w = block_sum(loc_rr, sh);
+        if (threadIdx.x == 0) { __stcg(part_rz + blockIdx.x, v); __stcg(part_rr + blockIdx.x, w); }
+        grid.sync();
+        const float rznew = grid_total(part_rz, sh);
+        res = grid_total(part_rr, sh);
+        if (it % a.check_every == 0) {
+            const bool finite = isfinite(res);
+            if (!finite || (double)res < a.toll_sq) {
+                if (!finite) flags |= 2;
+                break;
+            }
+        }
+        beta = rznew / rz;
+        rz = rznew;
+        cur ^= 1;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (own[k]) a.x[gid + k * ngroups] = xk[k];
+    if (niters >= a.maxiter) flags |= 1;
+    if (tid == 0 && a.info) {
+        a.info[0] = niters;
+        a.info[1] = __float_as_int(res);
+        a.info[2] = flags;
+        a.info[3] = 0;
+    }
+}
+
+__global__ void max_row_kernel(int n, const int32_t* __restrict__ rowptr, int* out) {
+    int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, rowptr[i + 1] - rowptr[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 // ---------------------------------------------------------------- explicit lumped step
 // Rows are LOCAL (0..n-1) and belong to global rows row_lo..row_lo+n-1 of a row-block partition;
 // columns, U_in and U_out are GLOBAL (every rank holds full-length U buffers of which only its own
@@ -292,6 +461,8 @@ int launch_expl(int G, const ExplArgs& a, unsigned nb, cudaStream_t s) {
 
 using namespace pdx;
 
+constexpr int PCG_SMALL_E = 2;     // entries per lane and row
+
 struct pdx_pcg {
     int n;
     int64_t nnz;
@@ -303,6 +474,9 @@ struct pdx_pcg {
     float* part;
     int G;
     int nblocks;
+    int max_row;     // longest row (selects the register-resident kernel)
+    bool small;      // rows per lane group <= 4 and rows <= 2 Gs entries: pcg_small_kernel<Gs, Ks, 2>
+    int Gs, Ks;
 };
 
 extern "C" {
@@ -356,6 +530,25 @@ int pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const f
         if (e && std::atoi(e) > 0) nb = std::min<long long>(std::atoi(e), (long long)sms * per_sm);
     }
     s->nblocks = (int)nb;
+    {   // longest row -> can the register-resident kernel take this system?  (one-time set-up read, like nnz above)
+        int* dmax = nullptr;
+        int hmax = 0;
+        if (check_cuda(cudaMalloc(&dmax, sizeof(int)), "cudaMalloc(max row)") ||
+            check_cuda(cudaMemset(dmax, 0, sizeof(int)), "clear max row")) { delete s; return 1; }
+        max_row_kernel<<<64, 256>>>(n, rowptr, dmax);
+        const bool bad = check_cuda(cudaMemcpy(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost), "read max row") != 0;
+        cudaFree(dmax);
+        if (bad) { delete s; return 1; }
+        s->max_row = hmax;
+        // lanes per row of the register-resident kernel: the fewest that hold a row in PCG_SMALL_E entries per lane
+        // (more groups = fewer rows per group = fewer registers), then 2 or 4 rows per group
+        s->Gs = hmax <= 4 * PCG_SMALL_E ? 4 : hmax <= 8 * PCG_SMALL_E ? 8 : hmax <= 16 * PCG_SMALL_E ? 16 : 32;
+        const long long ngroups = (long long)s->nblocks * 256 / s->Gs;
+        const long long rows_per_group = (n + ngroups - 1) / ngroups;
+        s->Ks = rows_per_group <= 2 ? 2 : 4;
+        const char* e = std::getenv("PDX_PCG_SMALL");           // A/B switch: PDX_PCG_SMALL=0 keeps the loop kernel
+        s->small = !(e && e[0] == '0') && rows_per_group <= 4 && hmax <= PCG_SMALL_E * s->Gs && s->nblocks <= sms * 4;
+    }
     if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 4 * (size_t)n), "cudaMalloc(pcg work)")) { delete s; return 1; }
     if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 3 * (size_t)s->nblocks), "cudaMalloc(pcg partials)")) {
         cudaFree(s->work); delete s; return 1;
@@ -399,11 +592,21 @@ static int pcg_launch(pdx_pcg* s, const float* b, const float* mval, const float
     a.info = info;
     void* args[] = {&a};
     const void* fn;
-    switch (s->G) {
-        case 4:  fn = (const void*)pcg_kernel<4>; break;
-        case 8:  fn = (const void*)pcg_kernel<8>; break;
-        case 16: fn = (const void*)pcg_kernel<16>; break;
-        default: fn = (const void*)pcg_kernel<32>; break;
+    if (s->small) {
+        const bool k2 = s->Ks == 2;
+        switch (s->Gs) {
+            case 4:  fn = k2 ? (const void*)pcg_small_kernel<4, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<4, 4, PCG_SMALL_E>; break;
+            case 8:  fn = k2 ? (const void*)pcg_small_kernel<8, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<8, 4, PCG_SMALL_E>; break;
+            case 16: fn = k2 ? (const void*)pcg_small_kernel<16, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<16, 4, PCG_SMALL_E>; break;
+            default: fn = k2 ? (const void*)pcg_small_kernel<32, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<32, 4, PCG_SMALL_E>; break;
+        }
+    } else {
+        switch (s->G) {
+            case 4:  fn = (const void*)pcg_kernel<4>; break;
+            case 8:  fn = (const void*)pcg_kernel<8>; break;
+            case 16: fn = (const void*)pcg_kernel<16>; break;
+            default: fn = (const void*)pcg_kernel<32>; break;
+        }
     }
     count_launch();
     return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(s->nblocks), dim3(256), args, 0, (cudaStream_t)stream),
