@@ -192,9 +192,10 @@ __global__ void __launch_bounds__(256) pcg_kernel(const __grid_constant__ PcgArg
 // has the same order and the iterates are bitwise those of pcg_kernel with the same grid.
 // Needs at most K rows per group and rows of at most E*G entries (checked by the host at pdx_pcg_create).
 template <int G, int K, int E>
-__global__ void __launch_bounds__(256, 4) pcg_small_kernel(const __grid_constant__ PcgArgs a) {
+__global__ void __launch_bounds__(256, K <= 2 ? 4 : (K <= 4 ? 2 : 1)) pcg_small_kernel(const __grid_constant__ PcgArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[33];
+    __shared__ float sh2[66];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int gid = tid / G, sub = threadIdx.x % G, ngroups = nthreads / G;
@@ -311,12 +312,11 @@ __global__ void __launch_bounds__(256, 4) pcg_small_kernel(const __grid_constant
                 loc_rz = fmaf(r, z, loc_rz);
             }
         }
-        v = block_sum(loc_rz, sh);
-        w = block_sum(loc_rr, sh);
+        block_sum2(loc_rz, loc_rr, sh2, v, w);              // both sums through one pair of block barriers
         if (threadIdx.x == 0) { __stcg(part_rz + blockIdx.x, v); __stcg(part_rr + blockIdx.x, w); }
         grid.sync();
-        const float rznew = grid_total(part_rz, sh);
-        res = grid_total(part_rr, sh);
+        float rznew;
+        grid_total2(part_rz, part_rr, sh2, rznew, res);
         if (it % a.check_every == 0) {
             const bool finite = isfinite(res);
             if (!finite || (double)res < a.toll_sq) {
@@ -543,11 +543,28 @@ int pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const f
         // lanes per row of the register-resident kernel: the fewest that hold a row in PCG_SMALL_E entries per lane
         // (more groups = fewer rows per group = fewer registers), then 2 or 4 rows per group
         s->Gs = hmax <= 4 * PCG_SMALL_E ? 4 : hmax <= 8 * PCG_SMALL_E ? 8 : hmax <= 16 * PCG_SMALL_E ? 16 : 32;
-        const long long ngroups = (long long)s->nblocks * 256 / s->Gs;
-        const long long rows_per_group = (n + ngroups - 1) / ngroups;
-        s->Ks = rows_per_group <= 2 ? 2 : 4;
         const char* e = std::getenv("PDX_PCG_SMALL");           // A/B switch: PDX_PCG_SMALL=0 keeps the loop kernel
-        s->small = !(e && e[0] == '0') && rows_per_group <= 4 && hmax <= PCG_SMALL_E * s->Gs && s->nblocks <= sms * 4;
+        const char* eb = std::getenv("PDX_PCG_BLOCKS");
+        const bool allowed = !(e && e[0] == '0') && hmax <= PCG_SMALL_E * s->Gs;
+        auto rows_per_group = [&](long long blocks) {
+            const long long ngroups = blocks * 256 / s->Gs;
+            return (n + ngroups - 1) / ngroups;
+        };
+        s->small = false;
+        if (allowed) {
+            // measured on config 1 (tools/tune_pcg_blocks.py): two blocks per SM with 4 rows per group beat four blocks per
+            // SM with 2 (cheaper grid barrier); without an override take the fewest blocks in {2, 4} x SMs that fit
+            long long cand[2] = {2LL * sms, 4LL * sms};
+            long long pick = 0;
+            if (eb && std::atoi(eb) > 0) pick = s->nblocks;
+            else for (long long c : cand) if (!pick && rows_per_group(c) <= 4) pick = c;
+            if (pick) {
+                const long long rpg = rows_per_group(pick);
+                const int K = rpg <= 2 ? 2 : rpg <= 4 ? 4 : 8;
+                const long long per = K == 2 ? 4 : K == 4 ? 2 : 1;          // launch bounds of pcg_small_kernel
+                if (rpg <= 8 && pick <= per * sms) { s->small = true; s->Ks = K; s->nblocks = (int)pick; }
+            }
+        }
     }
     if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 4 * (size_t)n), "cudaMalloc(pcg work)")) { delete s; return 1; }
     if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 3 * (size_t)s->nblocks), "cudaMalloc(pcg partials)")) {
@@ -593,13 +610,15 @@ static int pcg_launch(pdx_pcg* s, const float* b, const float* mval, const float
     void* args[] = {&a};
     const void* fn;
     if (s->small) {
-        const bool k2 = s->Ks == 2;
+#define PDX_SMALL_PICK(GG) (s->Ks == 2 ? (const void*)pcg_small_kernel<GG, 2, PCG_SMALL_E> : s->Ks == 4 ? \
+                           (const void*)pcg_small_kernel<GG, 4, PCG_SMALL_E> : (const void*)pcg_small_kernel<GG, 8, PCG_SMALL_E>)
         switch (s->Gs) {
-            case 4:  fn = k2 ? (const void*)pcg_small_kernel<4, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<4, 4, PCG_SMALL_E>; break;
-            case 8:  fn = k2 ? (const void*)pcg_small_kernel<8, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<8, 4, PCG_SMALL_E>; break;
-            case 16: fn = k2 ? (const void*)pcg_small_kernel<16, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<16, 4, PCG_SMALL_E>; break;
-            default: fn = k2 ? (const void*)pcg_small_kernel<32, 2, PCG_SMALL_E> : (const void*)pcg_small_kernel<32, 4, PCG_SMALL_E>; break;
+            case 4:  fn = PDX_SMALL_PICK(4); break;
+            case 8:  fn = PDX_SMALL_PICK(8); break;
+            case 16: fn = PDX_SMALL_PICK(16); break;
+            default: fn = PDX_SMALL_PICK(32); break;
         }
+#undef PDX_SMALL_PICK
     } else {
         switch (s->G) {
             case 4:  fn = (const void*)pcg_kernel<4>; break;

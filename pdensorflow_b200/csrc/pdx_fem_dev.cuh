@@ -45,6 +45,41 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
     return sh[32];
 }
 
+// Two block sums through one pair of block barriers (sh: 66 floats).  Same shuffle trees and the same order of the
+// per-warp partials as two block_sum calls, so the results are bitwise those of block_sum.
+__device__ __forceinline__ void block_sum2(float a, float b, float* sh, float& ra, float& rb) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sh[w] = a; sh[33 + w] = b; }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    if (w == 0) {
+        float t = lane < nw ? sh[lane] : 0.0f;
+        float u = lane < nw ? sh[33 + lane] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+            u += __shfl_xor_sync(0xffffffffu, u, o);
+        }
+        if (lane == 0) { sh[32] = t; sh[65] = u; }
+    }
+    __syncthreads();
+    ra = sh[32];
+    rb = sh[65];
+}
+
+// grid_total of two partial arrays in one pass
+__device__ __forceinline__ void grid_total2(const float* pa, const float* pb, float* sh, float& ra, float& rb) {
+    float v = 0.0f, w = 0.0f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { v += __ldcg(pa + i); w += __ldcg(pb + i); }
+    block_sum2(v, w, sh, ra, rb);
+}
+
 // Sum of the per-block partials, same order in every block => every block gets the same bits.
 __device__ __forceinline__ float grid_total(const float* part, float* sh) {
     float v = 0.0f;

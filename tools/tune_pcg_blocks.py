@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-for nb in (0, 74, 148, 222, 296, 444, 592, 888):
+for nb in (0, 148, 222, 296, 444, 592):
     env = dict(os.environ)
     if nb:
         env['PDX_PCG_BLOCKS'] = str(nb)
