@@ -552,12 +552,14 @@ int pdx_pcg_create(int32_t n, const int32_t* rowptr, const int32_t* col, const f
         };
         s->small = false;
         if (allowed) {
-            // measured on config 1 (tools/tune_pcg_blocks.py): two blocks per SM with 4 rows per group beat four blocks per
-            // SM with 2 (cheaper grid barrier); without an override take the fewest blocks in {2, 4} x SMs that fit
-            long long cand[2] = {2LL * sms, 4LL * sms};
+            // measured on config 1 (tools/tune_pcg_blocks.py, r02g): 148 blocks x 8 rows per group 0.080 ms per step,
+            // 296 x 4: 0.083, 592 x 2: 0.097 - the grid barrier gets cheaper faster than the phases get longer.
+            // Without an override take the fewest blocks in {1, 2, 4} x SMs whose rows per group fit the registers.
+            const long long cand[3] = {1LL * sms, 2LL * sms, 4LL * sms};
+            const long long cap[3] = {8, 4, 2};
             long long pick = 0;
             if (eb && std::atoi(eb) > 0) pick = s->nblocks;
-            else for (long long c : cand) if (!pick && rows_per_group(c) <= 4) pick = c;
+            else for (int c = 0; c < 3; ++c) if (!pick && rows_per_group(cand[c]) <= cap[c]) pick = cand[c];
             if (pick) {
                 const long long rpg = rows_per_group(pick);
                 const int K = rpg <= 2 ? 2 : rpg <= 4 ? 4 : 8;
