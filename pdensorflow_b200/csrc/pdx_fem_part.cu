@@ -75,9 +75,8 @@ struct PartArgs {
     const float* b;                  // n (used when mval == null)
     const float* rhs0;               // window (used when mval != null)
     float* x;                        // window
-    float* p;                        // window (peer visible: the neighbours store their first direction into its ghosts)
-    float* p2;                       // window, local: second direction buffer
-    float* zg;                       // window: z = Minv r, owned part written here, ghost parts by the neighbours
+    float* p;                        // window
+    float* zg;                       // window; only the ghost parts are used
     float *r, *q;                    // n
     float* part;                     // 2 buffers x 2 scalars x gridDim.x
     Comm* comm;
@@ -174,9 +173,8 @@ __device__ __forceinline__ bool all_reduce(const PartArgs& a, cg::grid_group& gr
 // by the lane that owns it (mv == nullptr: the second product is skipped and 0 is passed).
 //  G > 0: CSR, G lanes per row.   G == 0: SELL-32 (a.rowptr = slice_ptr): a warp per 32-row slice, one
 //  thread per row, column-major inside the slice so that every col/val access is a coalesced 128-byte load.
-template <int G, class GV, class F>
-__device__ __forceinline__ void rows_dot(const PartArgs& a, GV&& gv, const float* mv, const float* xm, F&& f) {
-    // gv(c) = value of the multiplied vector at window column c (a plain gather, or the direction formed on the fly)
+template <int G, class F>
+__device__ __forceinline__ void rows_dot(const PartArgs& a, const float* xa, const float* mv, const float* xm, F&& f) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     if constexpr (G == 0) {
@@ -189,12 +187,12 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, GV&& gv, const float
 #pragma unroll 2
                 for (int k = beg + lane; k < end; k += 32) {
                     const int c = a.col[k];
-                    acc = fmaf(a.aval[k], gv(c), acc);
+                    acc = fmaf(a.aval[k], __ldcg(xa + c), acc);
                     accm = fmaf(mv[k], __ldcg(xm + c), accm);
                 }
             } else {
 #pragma unroll 4
-                for (int k = beg + lane; k < end; k += 32) acc = fmaf(a.aval[k], gv(a.col[k]), acc);
+                for (int k = beg + lane; k < end; k += 32) acc = fmaf(a.aval[k], __ldcg(xa + a.col[k]), acc);
             }
             const int row = sl * 32 + lane;
             if (row < a.n) f(row, acc, accm);
@@ -205,10 +203,7 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, GV&& gv, const float
         for (int row = gid; row < nround; row += ngroups) {
             const bool valid = row < a.n;
             const int beg = valid ? a.rowptr[row] : 0, end = valid ? a.rowptr[row + 1] : 0;
-            float acc = 0.0f;
-            for (int k = beg + sub; k < end; k += G) acc = fmaf(a.aval[k], gv(a.col[k]), acc);
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
+            const float acc = row_dot<(G > 0 ? G : 1)>(a.col, a.aval, xa, beg, end, sub, true);
             float accm = 0.0f;
             if (mv) accm = row_dot<(G > 0 ? G : 1)>(a.col, mv, xm, beg, end, sub, true);   // uniform branch
             if (valid && sub == 0) f(row, acc, accm);
@@ -217,7 +212,7 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, GV&& gv, const float
 }
 
 template <int G>
-__global__ void __launch_bounds__(256, G == 0 ? 8 : 4) pcg_part_kernel(const __grid_constant__ PartArgs a) {
+__global__ void __launch_bounds__(256, 8) pcg_part_kernel(const __grid_constant__ PartArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[33];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,7 +224,7 @@ __global__ void __launch_bounds__(256, G == 0 ? 8 : 4) pcg_part_kernel(const __g
     // b = M rhs0 (optional) ; r = b - A x ; z = Minv r ; p = z ; rz = r.z      (conjgrad.py:191-203)
     float loc_rz = 0.0f, loc_rr = 0.0f;
     bool pushed = false;
-    rows_dot<G>(a, [&](int c) { return __ldcg(a.x + c); }, a.mval, a.rhs0, [&](int row, float ax, float bm) {
+    rows_dot<G>(a, a.x, a.mval, a.rhs0, [&](int row, float ax, float bm) {
         const float bv = a.mval ? bm : a.b[row];
         const float r = __fsub_rn(bv, ax);
         const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
@@ -243,38 +238,15 @@ __global__ void __launch_bounds__(256, G == 0 ? 8 : 4) pcg_part_kernel(const __g
     float rz, res;
     bool ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rz, &res, pushed);
 
-    // TWO all-reduces (= two grid barriers) per iteration.  The direction update p_k = z_{k-1} + beta p_{k-1}
-    // (conjgrad.py:184-187) is folded into the SpMV: every gathered column forms it on the fly from p_{k-1} and
-    // z_{k-1} = Minv r_{k-1} (both windows: owned part written by this rank, ghost part by the neighbours / recomputed
-    // here), with the fma the owner uses; the owner stores p_k of its rows into the OTHER p buffer, the ghost part of
-    // that buffer is recomputed the same way.  One streaming pass and one barrier less than the three-phase loop,
-    // bitwise the same iterates.  zg carries z for the whole window now.
-    int niters = 0, flags = 0, cur = 0;
-    float* pbuf[2] = {a.p, a.p2};
-    float beta = 0.0f;
+    int niters = 0, flags = 0;
     for (int k = 1; ok && k <= a.maxiter; ++k) {
         niters = k;
-        const float* pold = pbuf[cur];
-        float* pnew = pbuf[cur ^ 1];
-        const bool first = k == 1;
         // q = A p ; pq = p.q
         float loc_pq = 0.0f;
-        rows_dot<G>(a, [&](int c) {
-            const float pj = __ldcg(pold + c);
-            return first ? pj : fmaf(beta, pj, __ldcg(a.zg + c));
-        }, nullptr, nullptr, [&](int row, float ap, float) {
-            float pi = __ldcg(pold + glo + row);
-            if (!first) pi = fmaf(beta, pi, __ldcg(a.zg + glo + row));
-            __stcg(pnew + glo + row, pi);
+        rows_dot<G>(a, a.p, nullptr, nullptr, [&](int row, float ap, float) {
             __stcg(a.q + row, ap);
-            loc_pq = fmaf(pi, ap, loc_pq);
+            loc_pq = fmaf(__ldcg(a.p + glo + row), ap, loc_pq);
         });
-        // ghost part of p_k, recomputed exactly as its owner computes it
-        for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
-            const int w = g < a.glo ? g : a.n + g;
-            const float pg = __ldcg(pold + w);
-            __stcg(pnew + w, first ? pg : fmaf(beta, pg, __ldcg(a.zg + w)));
-        }
         float pq, unused;
         ok = all_reduce<1>(a, grid, epoch, sh, loc_pq, 0.0f, &pq, &unused, false);
         if (!ok) break;
@@ -283,12 +255,11 @@ __global__ void __launch_bounds__(256, G == 0 ? 8 : 4) pcg_part_kernel(const __g
         loc_rz = 0.0f; loc_rr = 0.0f;
         pushed = false;
         for (int i = tid; i < a.n; i += nthreads) {
-            const float pi = __ldcg(pnew + glo + i);
+            const float pi = __ldcg(a.p + glo + i);
             __stcg(a.x + glo + i, fmaf(alpha, pi, __ldcg(a.x + glo + i)));
             const float r = fmaf(-alpha, __ldcg(a.q + i), __ldcg(a.r + i));
             __stcg(a.r + i, r);
             const float z = a.minv ? __fmul_rn(a.minv[i], r) : r;
-            __stcg(a.zg + glo + i, z);
             if (i < a.send_lo) { a.peer_lo_zg[i] = z; pushed = true; }            // edge rows: z into the neighbours' ghost slots
             if (i >= hi_first) { a.peer_hi_zg[i - hi_first] = z; pushed = true; }
             loc_rr = fmaf(r, r, loc_rr);
@@ -297,13 +268,12 @@ __global__ void __launch_bounds__(256, G == 0 ? 8 : 4) pcg_part_kernel(const __g
         // ghost x, recomputed exactly as its owner computes it
         for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
             const int w = g < a.glo ? g : a.n + g;
-            __stcg(a.x + w, fmaf(alpha, __ldcg(pnew + w), __ldcg(a.x + w)));
+            __stcg(a.x + w, fmaf(alpha, __ldcg(a.p + w), __ldcg(a.x + w)));
         }
         float rznew;
         ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rznew, &res, pushed);
         if (!ok) break;
-        // batched convergence test + NaN/Inf guard (conjgrad.py:293-300); nothing is written after the last exchange
-        // of a solve (a neighbour may already be in its next one)
+        // batched convergence test + NaN/Inf guard (conjgrad.py:293-300); p is not needed after the last iteration
         if (k % a.check_every == 0) {
             const bool finite = isfinite(res);
             if (!finite || (double)res < a.toll_sq) {
@@ -312,9 +282,19 @@ __global__ void __launch_bounds__(256, G == 0 ? 8 : 4) pcg_part_kernel(const __g
             }
         }
         if (k == a.maxiter) break;
-        beta = rznew / rz;
+        const float beta = rznew / rz;
+        // p = z + beta p, owned rows and ghosts alike
+        for (int i = tid; i < a.n; i += nthreads) {
+            const float r = __ldcg(a.r + i);
+            const float z = a.minv ? __fmul_rn(a.minv[i], r) : r;
+            __stcg(a.p + glo + i, fmaf(beta, __ldcg(a.p + glo + i), z));
+        }
+        for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
+            const int w = g < a.glo ? g : a.n + g;
+            __stcg(a.p + w, fmaf(beta, __ldcg(a.p + w), __ldcg(a.zg + w)));
+        }
         rz = rznew;
-        cur ^= 1;
+        grid.sync();
     }
     if (!ok) flags |= 4;
     if (niters >= a.maxiter) flags |= 1;
@@ -346,7 +326,6 @@ struct pdx_pcg_part {
     char* ws;               // own workspace
     float *p, *zg;          // windows inside the workspace (written by the neighbours)
     float* work;            // r, q
-    float* p2;              // second direction window (local)
     float* part;
     PartArgs base;
 };
@@ -422,20 +401,18 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     s->p    = (float*)(s->ws + COMM_BYTES);
     s->zg   = (float*)(s->ws + COMM_BYTES + vec);
     if (check_cuda(cudaMalloc(&s->work, sizeof(float) * 2 * (size_t)d->n_local), "cudaMalloc(pcg_part work)")) { delete s; return 1; }
-    if (check_cuda(cudaMalloc(&s->p2, sizeof(float) * (size_t)window), "cudaMalloc(pcg_part p2)") ||
-        check_cuda(cudaMemset(s->p2, 0, sizeof(float) * (size_t)window), "clear p2")) { cudaFree(s->work); delete s; return 1; }
     if (check_cuda(cudaMalloc(&s->part, sizeof(float) * 4 * (size_t)s->nblocks), "cudaMalloc(pcg_part partials)")) {
-        cudaFree(s->work); cudaFree(s->p2); delete s; return 1;
+        cudaFree(s->work); delete s; return 1;
     }
     if (check_cuda(cudaMemset(s->ws, 0, COMM_BYTES + 2 * vec), "clear comm block") ||     // comm, p, zg
         check_cuda(cudaDeviceSynchronize(), "clear comm block (sync)")) {
-        cudaFree(s->work); cudaFree(s->part); cudaFree(s->p2); delete s; return 1;
+        cudaFree(s->work); cudaFree(s->part); delete s; return 1;
     }
     PartArgs& a = s->base;
     a = PartArgs{};
     a.n = d->n_local; a.glo = d->ghost_lo; a.ghi = d->ghost_hi;
     a.rowptr = d->rowptr; a.col = d->col; a.aval = d->aval; a.mval = d->mval; a.minv = d->minv;
-    a.p = s->p; a.p2 = s->p2; a.zg = s->zg;
+    a.p = s->p; a.zg = s->zg;
     a.r = s->work; a.q = s->work + d->n_local;
     a.part = s->part;
     a.comm = (Comm*)s->ws;
@@ -461,7 +438,6 @@ void pdx_pcg_part_destroy(pdx_pcg_part* s) {
     if (!s) return;
     cudaFree(s->work);
     cudaFree(s->part);
-    cudaFree(s->p2);
     delete s;
 }
 
