@@ -397,6 +397,7 @@ def run_ours(args):
             'sustained': sustained,
             'e2e': {'value': e2e_value, 'unit': 'Gnode-steps/s', 'h2d_bytes_per_step': frame_bytes,
                     'd2h_bytes_per_step': frame_bytes, 'steps': ke, 'simulations': 1,
+                    'host_link_gbs_per_direction_all_gpus': frame_bytes * ke / (ms_e * 1e-3) / 1e9,
                     'kernel_launches_per_step_per_rank': e2e_launches, 'what': e2e_what},
             'gpu_launches': launches,
             'parity': parity,

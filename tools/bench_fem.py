@@ -64,6 +64,8 @@ def main():
                           'nnz_per_row': round(rbar, 2), 'algorithmic_bytes_per_node_step': round(bpn, 1),
                           'algorithmic_gbs_per_gpu': round(n / world * bpn / ms / 1e6, 1), 'setup_s_per_rank': round(setup, 1),
                           'ghost_rows_sent': [fem.send_lo, fem.send_hi], 'finite': ok, 'layout': args.layout,
+                          'parity': 'UNPINNED: the explicit lumped step has no reference implementation (SURVEY 8a row E); '
+                                    'checked against the oracle restatement only (tests/test_fem_dist_gpu.py)',
                           'sell_padding': round(getattr(fem, 'padding', 1.0), 4)}), flush=True)
     if world > 1:
         dist.barrier()
