@@ -115,7 +115,10 @@ class ClockSampler:
                 'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def workload(n_gpus):
+def workload(n_gpus, strong=False):
+    if strong:
+        return {'name': 'config 4 (STRONG scaling): 3-D FD Fenton-Karma, the full 2048x2048x1024 grid stored [1024,2048,2048] '
+                        '(86 GB of state) split into %d x-slab(s)' % n_gpus, 'global': (1024, SLAB[1], SLAB[2])}
     if n_gpus == 1:
         return {'name': 'config 3: 3-D FD Fenton-Karma 512^3, fp32, 1 GPU', 'global': (512, 512, 512)}
     return {'name': 'config 4 (weak scaling): 3-D FD Fenton-Karma, 128 planes of 2048x2048 per GPU, z-slab halo '
@@ -259,7 +262,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
-    wl = workload(world)
+    wl = workload(world, args.strong)
     G = wl['global']
 
     def barrier():
@@ -335,7 +338,11 @@ def run_ours(args):
 
     # ---- e2e: ONE simulation, potential in pinned host memory between frames ------------------------------
     ke = max(3, min(args.steps, 10))
-    if world == 1:
+    e2e_value = frame_bytes = e2e_launches = None
+    e2e_what = 'skipped (--strong: the 17 GB frames are not part of the strong-scaling record)'
+    if args.strong:
+        pass
+    elif world == 1:
         streamer = FrameStreamer(st, STEPS_PER_FRAME, nchunks=8, skew=True)
         e2e_what = ('ONE simulation; per frame (10 time steps): pinned-host U -> device in 8 plane chunks, time-skewed '
                     'x-march (80 range launches of the fused kernel) behind the arriving chunks, finished planes -> '
@@ -346,25 +353,27 @@ def run_ours(args):
         e2e_what = ('ONE simulation; per frame (10 time steps) and rank: pinned-host slab -> device in 8 plane chunks, '
                     '10 whole-slab fused steps (peer-memory halos), slab -> pinned host in 8 chunks; the next frame\'s '
                     'upload of a chunk starts when its download is done (PCIe duplex), NUMA-local pinned buffers')
-    for _ in range(2):
-        streamer.frame()
-    streamer.wait()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        streamer.frame()
-    streamer.wait()
-    torch.cuda.synchronize()
-    ms_e = allmax((time.perf_counter() - t0) * 1e3)      # three streams: the host clock around a full drain bounds it
-    barrier()
-    e2e_value = nodes_global * STEPS_PER_FRAME * ke / (ms_e * 1e-3) / 1e9
-    frame_bytes = streamer.frame_bytes
-    if world > 1:
-        fb = torch.tensor([frame_bytes], device=dev, dtype=torch.int64)
-        dist.all_reduce(fb, op=dist.ReduceOp.SUM)
-        frame_bytes = int(fb.item())
-    e2e_launches = streamer.launches_per_frame
-    del streamer
+    ms_e = None
+    if not args.strong:
+        for _ in range(2):
+            streamer.frame()
+        streamer.wait()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            streamer.frame()
+        streamer.wait()
+        torch.cuda.synchronize()
+        ms_e = allmax((time.perf_counter() - t0) * 1e3)      # three streams: the host clock around a full drain bounds it
+        barrier()
+        e2e_value = nodes_global * STEPS_PER_FRAME * ke / (ms_e * 1e-3) / 1e9
+        frame_bytes = streamer.frame_bytes
+        if world > 1:
+            fb = torch.tensor([frame_bytes], device=dev, dtype=torch.int64)
+            dist.all_reduce(fb, op=dist.ReduceOp.SUM)
+            frame_bytes = int(fb.item())
+        e2e_launches = streamer.launches_per_frame
+        del streamer
 
     # ---- parity of the timed launch path (every N) -----------------------------------------------------------
     parity = parity_check(fd, ds, G, rank, world, dev)
@@ -381,7 +390,7 @@ def run_ours(args):
         out = {
             'metric': 'Gnode-steps/s for 3D Fenton-Karma monodomain (fused FD step)',
             'value': value, 'unit': 'Gnode-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'global_grid': list(G), 'nodes': nodes_global,
                        'time_steps_per_bench_step': STEPS_PER_FRAME, 'ionic_model': 'fenton4v', 'dt': DT, 'diff': DIFF,
@@ -397,7 +406,7 @@ def run_ours(args):
             'sustained': sustained,
             'e2e': {'value': e2e_value, 'unit': 'Gnode-steps/s', 'h2d_bytes_per_step': frame_bytes,
                     'd2h_bytes_per_step': frame_bytes, 'steps': ke, 'simulations': 1,
-                    'host_link_gbs_per_direction_all_gpus': frame_bytes * ke / (ms_e * 1e-3) / 1e9,
+                    'host_link_gbs_per_direction_all_gpus': (frame_bytes * ke / (ms_e * 1e-3) / 1e9) if ms_e else None,
                     'kernel_launches_per_step_per_rank': e2e_launches, 'what': e2e_what},
             'gpu_launches': launches,
             'parity': parity,
@@ -412,7 +421,7 @@ def run_ours(args):
         }
         if dist_check is not None:
             out['parity']['distributed'] = dist_check
-    if world == 1:
+    if world == 1 and not args.strong:
         try:
             out['same_shape_n1'] = same_shape_n1(args)
         except Exception as e:
@@ -428,7 +437,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-        if rank == 0 and not args.skip_extras:
+        if rank == 0 and not args.skip_extras and not args.strong:
             # config 5 (row-block partitioned explicit FEM step) on the same N GPUs, after the process group of the
             # contract measurement is gone: its own torchrun, a record only
             try:
@@ -576,6 +585,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=os.environ.get('PDX_BENCH_WORKLOAD', 'fd'), choices=['fd', 'fem5', 'fem1', 'fd2d'])
+    ap.add_argument('--strong', action='store_true', help='strong scaling of config 4: the full 1024x2048x2048 grid at every N (no e2e / extras)')
     ap.add_argument('--verify', action='store_true', help='correctness checks only (parity + distributed bitwise), no timing')
     ap.add_argument('--skip-cpu', action='store_true', help='omit the cpu_baseline leg (profiling runs)')
     ap.add_argument('--skip-extras', action='store_true', help='omit the other_configs records (tools/ child processes)')
