@@ -74,11 +74,15 @@ def build(force=False, verbose=False):
                     raise RuntimeError('nvcc failed on %s' % name)
     objs = [os.path.join(BUILD, o) for _, o, _ in UNITS]
     if jobs or not os.path.exists(LIB):
-        cmd = [nvcc] + ARCH + ['-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC']
+        tmp = LIB + '.tmp.%d' % os.getpid()          # link beside the target, then rename: the library is replaced atomically
+        cmd = [nvcc] + ARCH + ['-shared', '-o', tmp] + objs + ['-Xcompiler', '-fPIC']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
+            if os.path.exists(tmp):
+                os.remove(tmp)
             raise RuntimeError('link failed')
+        os.replace(tmp, LIB)
     return LIB
 
 
