@@ -333,6 +333,10 @@ int     pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_worksp
                             int32_t max_window, pdx_pcg_part** out);
 void    pdx_pcg_part_destroy(pdx_pcg_part* s);
 int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s);
+/* Diagnostics: when device_stamps != NULL, thread 0 of every following solve writes %globaltimer (ns) at each phase
+ * boundary: [0] end of the set-up product, [1] after its all-reduce, then per iteration: end of q = A p, after the
+ * all-reduce, end of the x / r update, after the all-reduce, end of the p update, after the closing grid barrier. */
+int     pdx_pcg_part_set_profile(pdx_pcg_part* s, uint64_t* device_stamps, int32_t nstamps);
 /* Solve A x = b.  x: WINDOW (ghost_lo + n_local + ghost_hi floats): guess on entry - ghosts included,
  * they must equal the owners' values - solution on exit, ghosts kept equal to the owners' values by the
  * kernel.  b: n_local values, or NULL to use b = MASS * rhs0 with the rhs0 WINDOW (ghosts included:

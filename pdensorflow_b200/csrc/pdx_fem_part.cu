@@ -21,6 +21,7 @@
 //    involvement, no extra launch.  A rank that never shows up makes block 0 time out (timeout_ms) and
 //    the solve return flag bit 2 instead of hanging the GPU.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <new>
 #include "pdx_internal.h"
 #include "pdx_fem_dev.cuh"
@@ -61,6 +62,43 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// ---- L2 residency control (r02).  A CG iteration streams the matrix once (8 B per non-zero) and touches each of the
+// vectors p, r, q, x, Minv two to four times; at 4e6 rows the five vectors are 82 MB - they FIT the 126 MB L2, but the
+// 480 MB matrix stream evicts them between phases, so every vector access of the update phases went to DRAM
+// (52 of 170 B per row).  Matrix loads therefore carry an evict-first policy and vector accesses evict-last;
+// vectors beyond the budget (PartArgs::keep) keep the normal policy.
+typedef unsigned long long l2pol_t;
+__device__ __forceinline__ l2pol_t l2_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
+    l2pol_t p;
+    if (kind == 1)      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else                asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// vector accesses: L2-coherent (.cg, other SMs write these between grid barriers) + policy
+__device__ __forceinline__ float ldv(const float* a, l2pol_t pol) {
+    float v;
+    asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stv(float* a, float v, l2pol_t pol) {
+    asm volatile("st.global.cg.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+// matrix stream: read-only, never re-used inside an iteration
+__device__ __forceinline__ float ldm(const float* a, l2pol_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ldm(const int32_t* a, l2pol_t pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+struct Pol {
+    l2pol_t mat, p, r, q, x, minv;
+};
+
 __device__ __forceinline__ unsigned long long pack(unsigned int epoch, float v) {
     return ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
 }
@@ -90,6 +128,9 @@ struct PartArgs {
     double toll_sq;
     unsigned long long timeout_ns;
     int32_t* info;
+    unsigned long long* prof;        // optional: block 0 stamps %globaltimer at every phase boundary (diagnostics)
+    int nprof;
+    int keep;                        // L2 policy bits: 1 p, 2 r, 4 q, 8 x, 16 minv evict-last; 32 matrix evict-first
 };
 
 // All-reduce of NV (1 or 2) scalars over the ranks.  Returns false when a peer timed out.
@@ -174,7 +215,8 @@ __device__ __forceinline__ bool all_reduce(const PartArgs& a, cg::grid_group& gr
 //  G > 0: CSR, G lanes per row.   G == 0: SELL-32 (a.rowptr = slice_ptr): a warp per 32-row slice, one
 //  thread per row, column-major inside the slice so that every col/val access is a coalesced 128-byte load.
 template <int G, class F>
-__device__ __forceinline__ void rows_dot(const PartArgs& a, const float* xa, const float* mv, const float* xm, F&& f) {
+__device__ __forceinline__ void rows_dot(const PartArgs& a, const Pol& pol, l2pol_t polx, const float* xa, const float* mv,
+                                         const float* xm, F&& f) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     if constexpr (G == 0) {
@@ -183,16 +225,38 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, const float* xa, con
         for (int sl = tid >> 5; sl < nsl; sl += nthreads >> 5) {
             const int beg = a.rowptr[sl], end = a.rowptr[sl + 1];
             float acc = 0.0f, accm = 0.0f;
+            int k = beg + lane;
             if (mv) {
-#pragma unroll 2
-                for (int k = beg + lane; k < end; k += 32) {
-                    const int c = a.col[k];
-                    acc = fmaf(a.aval[k], __ldcg(xa + c), acc);
-                    accm = fmaf(mv[k], __ldcg(xm + c), accm);
+                for (; k + 32 < end; k += 64) {
+                    const int c0 = ldm(a.col + k, pol.mat), c1 = ldm(a.col + k + 32, pol.mat);
+                    const float v0 = ldm(a.aval + k, pol.mat), v1 = ldm(a.aval + k + 32, pol.mat);
+                    const float m0 = ldm(mv + k, pol.mat), m1 = ldm(mv + k + 32, pol.mat);
+                    const float x0 = ldv(xa + c0, polx), x1 = ldv(xa + c1, polx);
+                    const float y0 = __ldcg(xm + c0), y1 = __ldcg(xm + c1);
+                    acc = fmaf(v0, x0, acc);   accm = fmaf(m0, y0, accm);
+                    acc = fmaf(v1, x1, acc);   accm = fmaf(m1, y1, accm);
+                }
+                for (; k < end; k += 32) {
+                    const int c = ldm(a.col + k, pol.mat);
+                    acc = fmaf(ldm(a.aval + k, pol.mat), ldv(xa + c, polx), acc);
+                    accm = fmaf(ldm(mv + k, pol.mat), __ldcg(xm + c), accm);
                 }
             } else {
-#pragma unroll 4
-                for (int k = beg + lane; k < end; k += 32) acc = fmaf(a.aval[k], __ldcg(xa + a.col[k]), acc);
+                // four slice columns at a time: the matrix words first (plain read-only loads the compiler may hoist),
+                // then the four gathers they feed
+                for (; k + 96 < end; k += 128) {
+                    const int c0 = ldm(a.col + k, pol.mat), c1 = ldm(a.col + k + 32, pol.mat);
+                    const int c2 = ldm(a.col + k + 64, pol.mat), c3 = ldm(a.col + k + 96, pol.mat);
+                    const float v0 = ldm(a.aval + k, pol.mat), v1 = ldm(a.aval + k + 32, pol.mat);
+                    const float v2 = ldm(a.aval + k + 64, pol.mat), v3 = ldm(a.aval + k + 96, pol.mat);
+                    const float x0 = ldv(xa + c0, polx), x1 = ldv(xa + c1, polx);
+                    const float x2 = ldv(xa + c2, polx), x3 = ldv(xa + c3, polx);
+                    acc = fmaf(v0, x0, acc);
+                    acc = fmaf(v1, x1, acc);
+                    acc = fmaf(v2, x2, acc);
+                    acc = fmaf(v3, x3, acc);
+                }
+                for (; k < end; k += 32) acc = fmaf(ldm(a.aval + k, pol.mat), ldv(xa + ldm(a.col + k, pol.mat), polx), acc);
             }
             const int row = sl * 32 + lane;
             if (row < a.n) f(row, acc, accm);
@@ -212,7 +276,7 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, const float* xa, con
 }
 
 template <int G>
-__global__ void __launch_bounds__(256, 8) pcg_part_kernel(const __grid_constant__ PartArgs a) {
+__global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant__ PartArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[33];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,46 +284,66 @@ __global__ void __launch_bounds__(256, 8) pcg_part_kernel(const __grid_constant_
     const int glo = a.glo;
     const int hi_first = a.n - a.send_hi;          // first row the upper neighbour holds as a ghost
     unsigned int epoch = *((volatile unsigned int*)&a.comm->epoch);
+    Pol pol;
+    pol.mat  = l2_policy(a.keep & 32 ? 2 : 0);
+    pol.p    = l2_policy(a.keep & 1 ? 1 : 0);
+    pol.r    = l2_policy(a.keep & 2 ? 1 : 0);
+    pol.q    = l2_policy(a.keep & 4 ? 1 : 0);
+    pol.x    = l2_policy(a.keep & 8 ? 1 : 0);
+    pol.minv = l2_policy(a.keep & 16 ? 1 : 0);
 
     // b = M rhs0 (optional) ; r = b - A x ; z = Minv r ; p = z ; rz = r.z      (conjgrad.py:191-203)
     float loc_rz = 0.0f, loc_rr = 0.0f;
     bool pushed = false;
-    rows_dot<G>(a, a.x, a.mval, a.rhs0, [&](int row, float ax, float bm) {
+    rows_dot<G>(a, pol, pol.x, a.x, a.mval, a.rhs0, [&](int row, float ax, float bm) {
         const float bv = a.mval ? bm : a.b[row];
         const float r = __fsub_rn(bv, ax);
-        const float z = a.minv ? __fmul_rn(a.minv[row], r) : r;
-        __stcg(a.r + row, r);
-        __stcg(a.p + glo + row, z);
+        const float z = a.minv ? __fmul_rn(ldv(a.minv + row, pol.minv), r) : r;
+        stv(a.r + row, r, pol.r);
+        stv(a.p + glo + row, z, pol.p);
         if (row < a.send_lo) { a.peer_lo_p[row] = z; pushed = true; }          // the neighbours' ghost p = z
         if (row >= hi_first) { a.peer_hi_p[row - hi_first] = z; pushed = true; }
         loc_rz = fmaf(r, z, loc_rz);
         loc_rr = fmaf(r, r, loc_rr);
     });
+    int nstamp = 0;
+    auto stamp = [&]() {
+        if (a.prof && tid == 0 && nstamp < a.nprof) a.prof[nstamp] = global_ns();
+        ++nstamp;
+    };
+    stamp();
     float rz, res;
     bool ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rz, &res, pushed);
+    stamp();
 
     int niters = 0, flags = 0;
     for (int k = 1; ok && k <= a.maxiter; ++k) {
         niters = k;
         // q = A p ; pq = p.q
         float loc_pq = 0.0f;
-        rows_dot<G>(a, a.p, nullptr, nullptr, [&](int row, float ap, float) {
-            __stcg(a.q + row, ap);
-            loc_pq = fmaf(__ldcg(a.p + glo + row), ap, loc_pq);
+        rows_dot<G>(a, pol, pol.p, a.p, nullptr, nullptr, [&](int row, float ap, float) {
+            stv(a.q + row, ap, pol.q);
+            loc_pq = fmaf(ldv(a.p + glo + row, pol.p), ap, loc_pq);
         });
         float pq, unused;
+        stamp();
         ok = all_reduce<1>(a, grid, epoch, sh, loc_pq, 0.0f, &pq, &unused, false);
+        stamp();
         if (!ok) break;
         const float alpha = rz / pq;
         // x += alpha p ; r -= alpha q ; res = r.r ; z = Minv r ; rz' = r.z        (conjgrad.py:172-183)
         loc_rz = 0.0f; loc_rr = 0.0f;
         pushed = false;
         for (int i = tid; i < a.n; i += nthreads) {
-            const float pi = __ldcg(a.p + glo + i);
-            __stcg(a.x + glo + i, fmaf(alpha, pi, __ldcg(a.x + glo + i)));
-            const float r = fmaf(-alpha, __ldcg(a.q + i), __ldcg(a.r + i));
-            __stcg(a.r + i, r);
-            const float z = a.minv ? __fmul_rn(a.minv[i], r) : r;
+            const float pi = ldv(a.p + glo + i, pol.p);
+            const float xi = ldv(a.x + glo + i, pol.x);
+            const float qi = ldv(a.q + i, pol.q);
+            const float ri = ldv(a.r + i, pol.r);
+            const float mi = a.minv ? ldv(a.minv + i, pol.minv) : 1.0f;
+            stv(a.x + glo + i, fmaf(alpha, pi, xi), pol.x);
+            const float r = fmaf(-alpha, qi, ri);
+            stv(a.r + i, r, pol.r);
+            const float z = a.minv ? __fmul_rn(mi, r) : r;
             if (i < a.send_lo) { a.peer_lo_zg[i] = z; pushed = true; }            // edge rows: z into the neighbours' ghost slots
             if (i >= hi_first) { a.peer_hi_zg[i - hi_first] = z; pushed = true; }
             loc_rr = fmaf(r, r, loc_rr);
@@ -271,7 +355,9 @@ __global__ void __launch_bounds__(256, 8) pcg_part_kernel(const __grid_constant_
             __stcg(a.x + w, fmaf(alpha, __ldcg(a.p + w), __ldcg(a.x + w)));
         }
         float rznew;
+        stamp();
         ok = all_reduce<2>(a, grid, epoch, sh, loc_rz, loc_rr, &rznew, &res, pushed);
+        stamp();
         if (!ok) break;
         // batched convergence test + NaN/Inf guard (conjgrad.py:293-300); p is not needed after the last iteration
         if (k % a.check_every == 0) {
@@ -285,16 +371,19 @@ __global__ void __launch_bounds__(256, 8) pcg_part_kernel(const __grid_constant_
         const float beta = rznew / rz;
         // p = z + beta p, owned rows and ghosts alike
         for (int i = tid; i < a.n; i += nthreads) {
-            const float r = __ldcg(a.r + i);
-            const float z = a.minv ? __fmul_rn(a.minv[i], r) : r;
-            __stcg(a.p + glo + i, fmaf(beta, __ldcg(a.p + glo + i), z));
+            const float r = ldv(a.r + i, pol.r);
+            const float pi = ldv(a.p + glo + i, pol.p);
+            const float z = a.minv ? __fmul_rn(ldv(a.minv + i, pol.minv), r) : r;
+            stv(a.p + glo + i, fmaf(beta, pi, z), pol.p);
         }
         for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
             const int w = g < a.glo ? g : a.n + g;
             __stcg(a.p + w, fmaf(beta, __ldcg(a.p + w), __ldcg(a.zg + w)));
         }
         rz = rznew;
+        stamp();
         grid.sync();
+        stamp();
     }
     if (!ok) flags |= 4;
     if (niters >= a.maxiter) flags |= 1;
@@ -322,7 +411,7 @@ struct pdx_pcg_part {
     pdx_pcg_part_desc d;
     int window;
     int64_t nnz;
-    int G, nblocks;
+    int G, nblocks, nthreads;
     char* ws;               // own workspace
     float *p, *zg;          // windows inside the workspace (written by the neighbours)
     float* work;            // r, q
@@ -372,27 +461,32 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     s->nnz = last;
     s->G = d->sell ? 0 : pick_group(d->n_local, s->nnz);
     int dev = 0, sms = 0, per_sm = 0;
+    // threads per block: big systems run 1024 (a quarter of the arrivals at every grid barrier and of the block partials every
+    // block adds up; same 32-register budget and occupancy as 8 x 256), small ones 256.  PDX_PCG_PART_THREADS overrides.
+    int bt = (long long)d->n_local * (s->G > 0 ? s->G : 1) >= 1000000LL ? 1024 : 256;
+    if (const char* e = getenv("PDX_PCG_PART_THREADS")) { const int v = atoi(e); if (v == 256 || v == 512 || v == 1024) bt = v; }
+    s->nthreads = bt;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e;
     switch (s->G) {
-        case 0:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<0>, 256, 0); break;
-        case 4:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<4>, 256, 0); break;
-        case 8:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<8>, 256, 0); break;
-        case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<16>, 256, 0); break;
-        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<32>, 256, 0); break;
+        case 0:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<0>, bt, 0); break;
+        case 4:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<4>, bt, 0); break;
+        case 8:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<8>, bt, 0); break;
+        case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<16>, bt, 0); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<32>, bt, 0); break;
     }
     if (check_cuda(e, "occupancy query") || per_sm < 1) {
         if (per_sm < 1) set_error("pcg_part kernel cannot be resident");
         delete s; return 1;
     }
     const int lanes = s->G > 0 ? s->G : 1;
-    long long want = ((long long)d->n_local * lanes + 255) / 256;
+    long long want = ((long long)d->n_local * lanes + bt - 1) / bt;
     // big systems are bandwidth bound: fill the SMs; small ones are latency bound: one block per SM keeps the
     // grid barrier cheap
     long long cap = (long long)sms * per_sm;
     long long nb = want < cap ? want : cap;
-    if (nb > sms && (long long)d->n_local * lanes <= (long long)sms * 256 * 8) nb = sms;
+    if (nb > sms && (long long)d->n_local * lanes <= (long long)sms * 256 * 8) nb = sms;   // (bt == 256 here)
     if (d->max_blocks > 0 && nb > d->max_blocks) nb = d->max_blocks;
     if (nb < 1) nb = 1;
     s->nblocks = (int)nb;
@@ -430,6 +524,18 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     }
     a.rank = d->rank; a.world = d->world;
     a.timeout_ns = (unsigned long long)(d->timeout_ms > 0 ? d->timeout_ms : 10000) * 1000000ull;
+    // L2 residency: vectors that fit ~3/4 of the L2 (in order of re-use: p, r, q, x, Minv) are kept with evict-last,
+    // the matrix streams through with evict-first.  PDX_PCG_L2KEEP=<bits> overrides (0 = plain loads, for A/B runs).
+    {
+        int l2bytes = 0;
+        cudaDeviceGetAttribute(&l2bytes, cudaDevAttrL2CacheSize, dev);
+        const double budget = 0.75 * (double)l2bytes, vec_bytes = 4.0 * (double)window;
+        int keep = 32, nfit = vec_bytes > 0 ? (int)(budget / vec_bytes) : 5;
+        static const int order[5] = {1, 2, 4, 8, 16};
+        for (int i = 0; i < 5 && i < nfit; ++i) keep |= order[i];
+        if (const char* e = getenv("PDX_PCG_L2KEEP")) keep = atoi(e);
+        a.keep = keep;
+    }
     *out = s;
     return 0;
 }
@@ -442,6 +548,13 @@ void pdx_pcg_part_destroy(pdx_pcg_part* s) {
 }
 
 int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s) { return s ? s->nblocks : 0; }
+
+int pdx_pcg_part_set_profile(pdx_pcg_part* s, uint64_t* device_stamps, int32_t nstamps) {
+    if (!s) { set_error("pdx_pcg_part_set_profile: null handle"); return 1; }
+    s->base.prof = (unsigned long long*)device_stamps;
+    s->base.nprof = device_stamps ? nstamps : 0;
+    return 0;
+}
 
 int pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, const float* rhs0, float* x, int maxiter, double toll,
                        int check_every, int32_t* info, void* stream) {
@@ -469,7 +582,7 @@ int pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, const float* rhs0, float
         default: fn = (const void*)pcg_part_kernel<32>; break;
     }
     count_launch();
-    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(s->nblocks), dim3(256), args, 0, (cudaStream_t)stream),
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(s->nblocks), dim3(s->nthreads), args, 0, (cudaStream_t)stream),
                       "pcg_part_kernel cooperative launch");
 }
 

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--n', '--size', dest='n', type=int, default=160)
     ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--profile', action='store_true', help='print the phase durations of one solve (device %globaltimer stamps)')
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -59,15 +60,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     rbar = len(kv) / (hi - lo)
+    if args.profile and rank == 0:
+        from pdensorflow_b200 import _lib as L
+        stamps = torch.zeros(512, dtype=torch.int64, device='cuda')
+        L.check(L.lib().pdx_pcg_part_set_profile(fem._h, L.ptr(stamps), 512))
+        fem.step(1)
+        torch.cuda.synchronize()
+        L.check(L.lib().pdx_pcg_part_set_profile(fem._h, None, 0))
+        t = stamps.cpu().numpy()
+        t = t[t > 0]
+        d = np.diff(t) / 1e3
+        names = ['setup all-reduce'] + ['spmv', 'all-reduce 1', 'x/r update', 'all-reduce 2', 'p update', 'barrier'] * 64
+        per = {}
+        for nm, v in zip(names, d):
+            per.setdefault(nm, []).append(float(v))
+        print(json.dumps({'phase_us_median': {k: round(float(np.median(v)), 2) for k, v in per.items()},
+                          'solve_us': round(float(t[-1] - t[0]) / 1e3, 1), 'stamps': int(len(t))}), flush=True)
     it = float(np.mean(its))
     bpi = 44 + 8 * rbar                    # algorithmic bytes per node-iteration
+    bps = it * bpi + 32 + 2 * (8 * rbar + 12)   # per time step: + the ionic pass and the two set-up products (same table)
     if rank == 0:
         print(json.dumps({'workload': 'semi-implicit FK, structured tet mesh %d^3 = %d nodes, row-block x%d' % (args.n, n, world),
                           'n_gpus': world, 'ms_per_step': round(ms, 4), 'cg_iterations_per_step': it,
                           'us_per_cg_iteration': round(1e3 * ms / max(it, 1), 2),
                           'gnode_iterations_per_s': round(n * it / ms / 1e6, 2), 'gnode_steps_per_s': round(n / ms / 1e6, 3),
                           'nnz_per_row': round(rbar, 2), 'algorithmic_bytes_per_node_iteration': round(bpi, 1),
-                          'algorithmic_gbs_per_gpu': round(n / world * it * bpi / ms / 1e6, 1),
+                          'algorithmic_gbs_per_gpu_iterations_only': round(n / world * it * bpi / ms / 1e6, 1),
+                          'algorithmic_bytes_per_node_step': round(bps, 1),
+                          'algorithmic_gbs_per_gpu': round(n / world * bps / ms / 1e6, 1),
                           'cooperative_blocks': fem.blocks_per_grid, 'ghost_rows': [fem.glo, fem.ghi],
                           'setup_s_per_rank': round(setup, 1), 'finite': bool(torch.isfinite(fem.owned_U()).all())}), flush=True)
     if world > 1:
