@@ -176,6 +176,15 @@ int64_t pdx_fd_plan_launches(const pdx_fd_plan* p);
 int pdx_fd_step(pdx_fd_plan* p, float* U_a, float* U_b, float* const* states,
                 const float* DIFF, int nsteps, void* stream);
 int pdx_fd_plan_set_avec(pdx_fd_plan* p, const float* AVEC);
+/* PDX_LAP_ANISO on the TMA tile kernel (pdx_fd_aniso.cu).  laplace_heterogeneous_anisotropic_diffusion.py:40-45 forms
+ * C = sigma_t I + (sigma_l - sigma_t) a (x) a from DIFF / AVEC at every call; the fields are constants of a run, so
+ * pdx_fd_plan_prepare_aniso forms the six components once (same fp32 operations) into plan-owned [nx][ny][nz] arrays
+ * (stream ordered) and attaches AVEC.  Following pdx_fd_step* calls that pass the SAME DIFF pointer run the tile
+ * kernel; any other DIFF pointer, or a plan for which pdx_fd_plan_aniso_tile_capable() is 0 (nz % 4 != 0, Dirichlet
+ * pad, lookup-table model, kernel = GENERIC), keeps the one-thread-per-node kernel.  Call it again after changing
+ * the contents of DIFF or AVEC. */
+int pdx_fd_plan_aniso_tile_capable(const pdx_fd_plan* p);
+int pdx_fd_plan_prepare_aniso(pdx_fd_plan* p, const float* DIFF, const float* AVEC, void* stream);
 /* one step restricted to planes [xb, xe) (boundary-first / interior split used to
  * overlap the halo exchange); same clamps as the plan. */
 int pdx_fd_step_range(pdx_fd_plan* p, const float* U_in, float* U_out, float* const* states,

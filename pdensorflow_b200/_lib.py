@@ -85,6 +85,8 @@ _SIGNATURES = {
     'pdx_ionic_lut_step': (C.c_int, [C.POINTER(LutModel), C.c_int64, _P, C.POINTER(_P), _P, _P, _P, _P]),
     'pdx_fd_plan_set_lut': (C.c_int, [_P, C.POINTER(LutModel)]),
     'pdx_fd_plan_set_avec': (C.c_int, [_P, _P]),
+    'pdx_fd_plan_aniso_tile_capable': (C.c_int, [_P]),
+    'pdx_fd_plan_prepare_aniso': (C.c_int, [_P, _P, _P, _P]),
     'pdx_fd_laplace_aniso': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     'pdx_stim_apply': (C.c_int, [_P, _P, C.c_float, C.c_int64, _P]),
     'pdx_stim_apply_max': (C.c_int, [_P, _P, C.c_float, C.c_int64, _P]),

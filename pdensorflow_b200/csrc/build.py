@@ -19,7 +19,7 @@ LIB = os.path.join(PKG, 'libpdx.so')
 # (source, object, extra flags).  pdx_ionic_lut.cu is compiled TWICE: the EXACT kernels op-for-op (no FMA
 # contraction, IEEE division), the FAST kernels with contraction and approximate division (see its header).
 UNITS = [('pdx_api.cu', 'pdx_api.o', []), ('pdx_fd_generic.cu', 'pdx_fd_generic.o', []),
-         ('pdx_fd_tma.cu', 'pdx_fd_tma.o', []), ('pdx_fd_resident.cu', 'pdx_fd_resident.o', []),
+         ('pdx_fd_tma.cu', 'pdx_fd_tma.o', []), ('pdx_fd_aniso.cu', 'pdx_fd_aniso.o', []), ('pdx_fd_resident.cu', 'pdx_fd_resident.o', []),
          ('pdx_fem.cu', 'pdx_fem.o', []), ('pdx_fem_assemble.cu', 'pdx_fem_assemble.o', []), ('pdx_fem_sell.cu', 'pdx_fem_sell.o', []), ('pdx_fem_part.cu', 'pdx_fem_part.o', []),
          ('pdx_ionic_lut.cu', 'pdx_ionic_lut.o', ['-fmad=false', '-DPDX_LUT_TU_MATH=0']),
          ('pdx_ionic_lut.cu', 'pdx_ionic_lut_fast.o', ['-fmad=true', '-prec-div=false', '-DPDX_LUT_TU_MATH=1'])]

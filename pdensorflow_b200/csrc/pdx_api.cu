@@ -126,9 +126,17 @@ struct pdx_fd_plan {
     unsigned int* res_flags;
     float* res_halo;
     unsigned int res_base;
+    // anisotropic operator on the tile kernel: tensor components formed once by pdx_fd_plan_prepare_aniso
+    bool aniso_tile_ok;
+    float* aniso_C;
+    const float* aniso_diff;
+    const float* aniso_avec;
+    int aniso_chunk;
+    CUtensorMap aniso_maps[6];
     ~pdx_fd_plan() {
         if (res_flags) cudaFree(res_flags);
         if (res_halo) cudaFree(res_halo);
+        if (aniso_C) cudaFree(aniso_C);
     }
 };
 
@@ -309,8 +317,11 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
     }
     const bool want_resident = kernel == PDX_KERNEL_RESIDENT;
     if (kernel == PDX_KERNEL_AUTO || want_resident) kernel = tma_ok ? PDX_KERNEL_TMA : PDX_KERNEL_GENERIC;
+    if (kernel == PDX_KERNEL_TMA && !tma_ok && d.lap_kind == PDX_LAP_ANISO && fd_aniso_tile_supported(d)) {
+        kernel = PDX_KERNEL_GENERIC;      // the tile kernel takes over once pdx_fd_plan_prepare_aniso has run
+    }
     if (kernel == PDX_KERNEL_TMA && !tma_ok) {
-        set_error("pdx_fd_plan_create: TMA kernel needs nz % 4 == 0, no Dirichlet, no EXACT conv");
+        set_error("pdx_fd_plan_create: TMA kernel needs nz % 4 == 0, no EXACT conv");
         return 1;
     }
     pdx_fd_plan* p = new (std::nothrow) pdx_fd_plan();
@@ -335,6 +346,14 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
         }
     }
     p->want_resident = want_resident;
+    p->aniso_tile_ok = fd_aniso_tile_supported(d) && d.kernel != PDX_KERNEL_GENERIC;
+    {   // A/B switch: PDX_ANISO_TILE=0 keeps the anisotropic operator on the generic kernel
+        const char* e = std::getenv("PDX_ANISO_TILE");
+        if (e && e[0] == '0') p->aniso_tile_ok = false;
+    }
+    p->aniso_C = nullptr;
+    p->aniso_diff = p->aniso_avec = nullptr;
+    p->aniso_chunk = d.x_chunk > 0 ? d.x_chunk : fd_aniso_auto_chunk(d);
     p->has_lut = false;
     p->avec = nullptr;
     {   // states staged by TMA unless PDX_TMA_STATES=0 (A/B switch for profiling)
@@ -388,6 +407,34 @@ int pdx_fd_plan_set_avec(pdx_fd_plan* p, const float* AVEC) {
     p->avec = AVEC;
     return 0;
 }
+int pdx_fd_plan_aniso_tile_capable(const pdx_fd_plan* p) { return p && p->aniso_tile_ok ? 1 : 0; }
+
+int pdx_fd_plan_prepare_aniso(pdx_fd_plan* p, const float* DIFF, const float* AVEC, void* stream) {
+    if (!p || !DIFF || !AVEC) { set_error("pdx_fd_plan_prepare_aniso: null argument"); return 1; }
+    if (!p->aniso_tile_ok) {
+        set_error("pdx_fd_plan_prepare_aniso: the tile kernel takes 3-D grids with nz % 4 == 0, the closed-form models, "
+                  "no Dirichlet pad (and kernel != GENERIC)");
+        return 1;
+    }
+    const pdx_fd_desc& d = p->d;
+    const int64_t n = (int64_t)d.nx * d.ny * d.nz;
+    if (!p->aniso_C) {
+        if (check_cuda(cudaMalloc(&p->aniso_C, sizeof(float) * 6 * (size_t)n), "cudaMalloc(anisotropic tensor)")) return 1;
+        for (int c = 0; c < 6; ++c)
+            if (make_tensor_map_3d(&p->aniso_maps[c], p->aniso_C + (size_t)c * n, d.nx, d.ny, d.nz, 1, p->box_y, p->box_z)) return 1;
+    }
+    if (launch_aniso_tensor(DIFF, AVEC, p->aniso_C, n, (cudaStream_t)stream)) return 1;
+    p->aniso_diff = DIFF;
+    p->aniso_avec = AVEC;
+    p->avec = AVEC;
+    // opt in to the kernel's shared memory now, so that the first step may already be inside a graph capture
+    FdArgs a = p->base;
+    a.xb = a.xe = 0;
+    CUtensorMap dummy;
+    std::memset(&dummy, 0, sizeof(dummy));
+    return launch_fd_aniso_tile(d, a, dummy, p->aniso_maps, nullptr);
+}
+
 int pdx_fd_plan_kernel(const pdx_fd_plan* p) { return p ? (p->want_resident ? (int)PDX_KERNEL_RESIDENT : p->kernel) : -1; }
 int pdx_fd_plan_resident_capable(const pdx_fd_plan* p) { return p && p->resident_ok && p->resident_auto ? 1 : 0; }
 int64_t pdx_fd_plan_launches(const pdx_fd_plan* p) { return p ? p->launches : -1; }
@@ -419,6 +466,18 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
         const int rc = d.math_mode == PDX_MATH_FAST ? launch_fd_lut_fast(d, a, p->lut, s) : launch_fd_lut_exact(d, a, p->lut, s);
         if (!rc) p->launches += 1;
         return rc;
+    }
+    if (d.lap_kind == PDX_LAP_ANISO && p->aniso_C && DIFF == p->aniso_diff && p->avec == p->aniso_avec) {
+        bool aligned = ((uintptr_t)Uin % 16 == 0) && ((uintptr_t)Uout % 16 == 0);
+        for (int i = 0; i < ns; ++i) aligned = aligned && ((uintptr_t)states[i] % 16 == 0);
+        if (aligned) {
+            const CUtensorMap* mU = nullptr;
+            if (get_map(p, Uin, &mU)) return 1;
+            a.x_chunk = p->aniso_chunk;
+            const int rc = launch_fd_aniso_tile(d, a, *mU, p->aniso_maps, s);
+            if (!rc) p->launches += 1;
+            return rc;
+        }
     }
     int kernel = p->kernel;
     if (kernel == PDX_KERNEL_TMA) {

@@ -13,6 +13,7 @@
 // when reading shared memory: plane/row indices are clamped before addressing, z edges are
 // patched in registers (only in tiles that touch the boundary).
 #include "pdx_internal.h"
+#include "pdx_tma.cuh"
 
 namespace pdx {
 
@@ -41,64 +42,6 @@ struct Geo {
     static constexpr int BAR_OFF = STAGES * SLOT_BYTES + SRING_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + (STAGES + SSTAGES) * 8;
 };
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-// TMA: 3-D tiled bulk tensor load global -> shared, completion on an mbarrier
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                            uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
-}
-
-struct F4 {
-    float v[4];
-};
-__device__ __forceinline__ F4 lds4(const float* p) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    return F4{{t.x, t.y, t.z, t.w}};
-}
-__device__ __forceinline__ F4 ldg4(const float* p) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    return F4{{t.x, t.y, t.z, t.w}};
-}
-__device__ __forceinline__ void stg4(float* p, const F4& a) {
-    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
-}
-// z-edge patch of the four centre columns of a row (index clamp to [zclo, zchi])
-__device__ __forceinline__ void zfix(F4& a, bool lo2, bool hi2) {
-    if (lo2) a.v[0] = a.v[1];
-    if (hi2) a.v[3] = a.v[2];
-}
 
 struct StateMaps {
     CUtensorMap m[PDX_MAX_STATES];
@@ -257,7 +200,9 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
         const float* Sc = slotU(jc);
         const float* Sm = HAS_X ? slotU(jc - qs) : Sc;      // array plane p - 1
         const float* Sp = HAS_X ? slotU(jc + qs) : Sc;      // array plane p + 1
-        const bool raw_diff = yb_tile || zb_tile || (HAS_X && (p < a.xclo || p > a.xchi));   // CTA uniform
+        // CTA uniform.  Dirichlet pad: the planes next to the clamp box read a replaced neighbour plane too
+        const bool raw_diff = yb_tile || zb_tile || (HAS_X && (p < a.xclo || p > a.xchi)) ||
+                              (HAS_X && a.dirichlet && (p - 1 < a.xclo || p + 1 > a.xchi));
 
         F4 stc[R][NS > 0 ? NS : 1];
         if (TST) {
@@ -288,7 +233,33 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             F4 raw = c;
             if (raw_diff) {
                 if (MODEL != PDX_MODEL_NONE) raw = ldg4(a.Uin + gi);
-                if (zb_tile) {
+                if (a.dirichlet) {
+                    // constant pad of LaplaceSolver (laplaceSolver.py:44-52): U0 is the boundary value wherever the
+                    // (plane, row, column) of a stencil point lies outside the clamp box; shared memory was addressed
+                    // with clamped (valid) indices, the values read there are replaced
+                    const float dv = a.dirichlet_value;
+                    const int g = gy[r];
+                    const bool pin = !HAS_X || (p >= a.xclo && p <= a.xchi);
+                    const bool pmi = HAS_X && p - 1 >= a.xclo && p - 1 <= a.xchi;
+                    const bool ppi = HAS_X && p + 1 >= a.xclo && p + 1 <= a.xchi;
+                    const bool yin = pin && g >= a.yclo && g <= a.ychi;
+                    const bool ymi = pin && g - 1 >= a.yclo && g - 1 <= a.ychi;
+                    const bool ypi = pin && g + 1 >= a.yclo && g + 1 <= a.ychi;
+                    const bool yx = g >= a.yclo && g <= a.ychi;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool zin = z + e >= a.zclo && z + e <= a.zchi;
+                        c.v[e]  = (yin && zin) ? c.v[e] : dv;
+                        ym.v[e] = (ymi && zin) ? ym.v[e] : dv;
+                        yp.v[e] = (ypi && zin) ? yp.v[e] : dv;
+                        if (HAS_X) {
+                            xm.v[e] = (pmi && yx && zin) ? xm.v[e] : dv;
+                            xp.v[e] = (ppi && yx && zin) ? xp.v[e] : dv;
+                        }
+                    }
+                    zl = (yin && z - 1 >= a.zclo && z - 1 <= a.zchi) ? zl : dv;
+                    zr = (yin && z + 4 >= a.zclo && z + 4 <= a.zchi) ? zr : dv;
+                } else if (zb_tile) {
                     zfix(c, lo2, hi2); zfix(ym, lo2, hi2); zfix(yp, lo2, hi2);
                     if (HAS_X) { zfix(xm, lo2, hi2); zfix(xp, lo2, hi2); }
                     zl = lo1 ? c.v[0] : zl;          // after zfix c.v[0] already holds the clamped value
@@ -419,7 +390,6 @@ int launch_het(bool het, int math, bool tst, const FdArgs& a, const CUtensorMap&
 
 bool fd_tma_supported(const pdx_fd_desc& d) {
     if (d.nz % 4 != 0 || d.nz < 4) return false;
-    if (d.dirichlet) return false;
     if (d.lap_kind == PDX_LAP_CONV && d.math_mode == PDX_MATH_EXACT) return false;   // different rounding order
     if (d.ny < 3) return false;
     return true;

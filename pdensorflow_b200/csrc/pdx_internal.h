@@ -96,6 +96,13 @@ int  make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int
 void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* box_y, int* box_z);
 int  fd_tma_auto_chunk(const pdx_fd_desc& d);
 
+// 19-point fibre-tensor operator on TMA tiles (pdx_fd_aniso.cu): the six tensor components as six [n] arrays C
+bool fd_aniso_tile_supported(const pdx_fd_desc& d);
+int  fd_aniso_auto_chunk(const pdx_fd_desc& d);
+int  launch_aniso_tensor(const float* DIFF, const float* AVEC, float* C, int64_t n, cudaStream_t s);
+int  launch_fd_aniso_tile(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mapU, const CUtensorMap* mapC /* 6 */,
+                          cudaStream_t s);
+
 // SM-resident multi-step kernel for 2-D grids (pdx_fd_resident.cu)
 #define PDX_RESIDENT_FLAG_STRIDE 32
 struct ResidentGeom {

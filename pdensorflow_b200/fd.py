@@ -217,6 +217,7 @@ class FDStepper:
             self.DIFF = self._to_device(DIFF, extra=(2,))
             self.AVEC = self._to_device(AVEC, extra=(6,))
             L.check(L.lib().pdx_fd_plan_set_avec(self._plan, L.ptr(self.AVEC)))
+            self.refresh_aniso_tensor()
         self._cur = 0            # 0: current U is Ua
         self._states_arr = L.ptr_array(self.states)
         self._graphs = {}
@@ -233,6 +234,18 @@ class FDStepper:
             pass
 
     # ---- data in/out -----------------------------------------------------------------
+    def refresh_aniso_tensor(self):
+        """lap='aniso': (re)form the six tensor components from DIFF / AVEC for the tile kernel (pdx_fd_aniso.cu).  Called
+        at construction; call it again after changing DIFF or AVEC in place.  Shapes the tile kernel does not take
+        (nz % 4 != 0, Dirichlet pad, kernel='generic') keep the one-thread-per-node kernel, which reads DIFF / AVEC itself."""
+        if self.AVEC is None:
+            return False
+        if not L.lib().pdx_fd_plan_aniso_tile_capable(self._plan):
+            return False
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pdx_fd_plan_prepare_aniso(self._plan, L.ptr(self.DIFF), L.ptr(self.AVEC), L.stream_ptr()))
+        return True
+
     def _to_device(self, A, extra=()):
         if isinstance(A, torch.Tensor):
             t = A.to(device=self.device, dtype=torch.float32)

@@ -237,6 +237,82 @@ def test_tma_and_generic_kernels_agree(cuda):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize('shape', [(12, 19, 132), (20, 24, 260), (33, 260)])
+@pytest.mark.parametrize('lap', ['homog', 'heterog'])
+@pytest.mark.parametrize('model', [None, 'fenton4v'])
+def test_dirichlet_pad_on_the_tma_kernel(cuda, shape, lap, model):
+    """LaplaceSolver's constant pad (laplaceSolver.py:44-52) on the TMA tile kernel: bitwise the generic kernel in EXACT
+    arithmetic, and the oracle's fd_step(dirichlet=...) within the EXACT tolerance."""
+    from pdensorflow_b200.fd import FDStepper
+    rng = np.random.default_rng(31)
+    U, states = random_fields(shape, seed=37)
+    states = states[:NSTATES[model]]
+    DIFF = (0.2 + rng.random(shape)).astype(np.float32) if lap == 'heterog' else None
+    spacing = (1.0, 0.9, 1.1)[:len(shape)]
+    res = {}
+    for kernel in ('tma', 'generic'):
+        st = FDStepper(shape, spacing, 0.05, 0.8, model=model, lap=lap, DIFF=DIFF, math='exact', kernel=kernel, dirichlet=3.5)
+        st.set_U(U)
+        if states:
+            st.set_states(states)
+        st.step(3)
+        res[kernel] = [st.U().cpu().numpy()] + [x.cpu().numpy() for x in st.states]
+    for a, b in zip(res['tma'], res['generic']):
+        assert np.array_equal(a, b)
+    m = make_oracle(model, 0.05, states)
+    Uo = U.copy()
+    for _ in range(3):
+        Uo = ofd.fd_step(m, Uo, 0.05, 0.8, spacing, DIFF=DIFF, dirichlet=3.5)
+    assert rel_l2(res['tma'][0].reshape(shape), Uo) <= TOL['exact']
+
+
+def _aniso_fields(shape, seed):
+    rng = np.random.default_rng(seed)
+    DF = np.empty(shape + (2,), np.float32)
+    DF[..., 0] = 0.1 + 0.2 * rng.random(shape)
+    DF[..., 1] = 0.5 * rng.random(shape)
+    a = rng.standard_normal(shape + (3,))
+    a /= np.linalg.norm(a, axis=-1, keepdims=True)
+    AV = np.stack([a[..., 0] * a[..., 0], a[..., 0] * a[..., 1], a[..., 0] * a[..., 2], a[..., 1] * a[..., 1],
+                   a[..., 1] * a[..., 2], a[..., 2] * a[..., 2]], axis=-1).astype(np.float32)
+    return DF, AV
+
+
+@pytest.mark.parametrize('shape,chunk', [((9, 11, 16), 0), ((21, 19, 132), 4), ((12, 24, 260), 5), ((3, 3, 4), 0)])
+@pytest.mark.parametrize('model', [None, 'fenton4v', 'mms2v'])
+def test_anisotropic_tile_kernel(cuda, shape, chunk, model):
+    """19-point fibre-tensor operator on TMA tiles (pdx_fd_aniso.cu): EXACT arithmetic is bitwise the one-thread-per-node
+    kernel (and the oracle within the EXACT tolerance) on partial tiles, several z tiles and x chunks with halo planes;
+    FAST stays within 1e-5."""
+    from pdensorflow_b200.fd import FDStepper
+    DF, AV = _aniso_fields(shape, 41)
+    U, states = random_fields(shape, seed=43)
+    states = states[:NSTATES[model]]
+    spacing, dt, nsteps = (1.0, 0.8, 1.25), 0.02, 3
+    res = {}
+    for tag, kernel, math in (('tile', 'auto', 'exact'), ('generic', 'generic', 'exact'), ('fast', 'auto', 'fast')):
+        st = FDStepper(shape, spacing, dt, 1.0, model=model, lap='aniso', DIFF=DF, AVEC=AV, math=math, kernel=kernel,
+                       x_chunk=chunk)
+        from pdensorflow_b200 import _lib as L
+        assert bool(L.lib().pdx_fd_plan_aniso_tile_capable(st._plan)) == (kernel != 'generic')
+        st.set_U(U)
+        if states:
+            st.set_states(states)
+        st.step(nsteps)
+        res[tag] = [st.U().cpu().numpy().reshape(shape)] + [x.cpu().numpy().reshape(shape) for x in st.states]
+    for a, b in zip(res['tile'], res['generic']):
+        assert np.array_equal(a, b)
+    m = make_oracle(model, dt, states)
+    Uo = U.copy()
+    for _ in range(nsteps):
+        U0 = ofd.enforce_boundary(Uo)
+        lap = ofd.laplace_heterog_aniso_3d(U0, DF, AV, *spacing)
+        dU = m.differentiate(Uo) if m is not None else np.float32(0.0)
+        Uo = (U0 + np.float32(dt) * dU + np.float32(dt) * lap).astype(np.float32)
+    assert rel_l2(res['tile'][0], Uo) <= TOL['exact']
+    assert rel_l2(res['fast'][0], Uo) <= TOL['fast']
+
+
 def test_x_chunking_is_invisible(cuda):
     """The TMA kernel marches x in chunks with 2 halo planes: results must not depend on the chunk."""
     from pdensorflow_b200.fd import FDStepper

@@ -28,11 +28,23 @@ def bench(shape, model='fenton4v', math='fast', kernel='auto', lap='homog', nste
     elif model == 'ttp':
         mobj, u_rest, dt, diff = TenTusscherPanfilov(), -86.2, 0.02, 0.1
     DIFF = torch.full(shape, diff, device='cuda') if lap == 'heterog' else None
-    st = FDStepper(shape, (1.0,) * len(shape), dt, diff, model=mobj, math=math, kernel=kernel, lap=lap, DIFF=DIFF)
+    AVEC = None
+    if lap == 'aniso':
+        # sigma_t = diff/4, sigma_l = diff, fibres rotating in the (x,y) plane with z: a full tensor at every node
+        DIFF = torch.empty(tuple(shape) + (2,), device='cuda')
+        DIFF[..., 0] = 0.25 * diff
+        DIFF[..., 1] = 0.75 * diff
+        ang = torch.linspace(0.0, 3.0, shape[2], device='cuda').view(1, 1, -1).expand(*shape)
+        a = torch.stack([torch.cos(ang), torch.sin(ang), 0.3 * torch.ones_like(ang)], dim=-1)
+        a = a / a.norm(dim=-1, keepdim=True)
+        AVEC = torch.stack([a[..., 0] * a[..., 0], a[..., 0] * a[..., 1], a[..., 0] * a[..., 2], a[..., 1] * a[..., 1],
+                            a[..., 1] * a[..., 2], a[..., 2] * a[..., 2]], dim=-1).contiguous()
+        del ang, a
+    st = FDStepper(shape, (1.0,) * len(shape), dt, diff, model=mobj, math=math, kernel=kernel, lap=lap, DIFF=DIFF, AVEC=AVEC)
     U = st.U()
     U.fill_(u_rest)
     U[0:2] = 20.0
-    st.step(20 if name in ('crn', 'ttp') else 200)
+    st.step(20 if name in ('crn', 'ttp') or lap == 'aniso' else 200)
     torch.cuda.synchronize()
     best = 1e9
     for _ in range(reps):
@@ -43,9 +55,12 @@ def bench(shape, model='fenton4v', math='fast', kernel='auto', lap='homog', nste
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / nsteps)
     n = int(np.prod(shape))
-    nb = BYTES[name] + (4 if lap == 'heterog' else 0)
+    # aniso: the tile kernel reads the six tensor components the plan formed once (24 B); the generic kernel reads DIFF
+    # [.,2] + AVEC [.,6] as the reference passes them (32 B)
+    tile = lap == 'aniso' and kernel != 'generic' and os.environ.get('PDX_ANISO_TILE', '1') != '0'
+    nb = BYTES[name] + (4 if lap == 'heterog' else 0) + ((24 if tile else 32) if lap == 'aniso' else 0)
     assert bool(torch.isfinite(st.U()).all())
-    print(json.dumps({'grid': list(shape), 'model': name or 'heat', 'lap': lap, 'math': math, 'kernel': st.kernel,
+    print(json.dumps({'grid': list(shape), 'model': name or 'heat', 'lap': lap, 'math': math, 'kernel': ('aniso-tile' if tile else st.kernel),
                       'ms_per_step': round(best, 4), 'gnode_steps_per_s': round(n / best / 1e6, 2),
                       'bytes_per_node_step': nb, 'algorithmic_gbs': round(n * nb / best / 1e6, 1),
                       'frac_of_measured_hbm_peak': round(n * nb / best / 1e6 / PEAK, 3)}), flush=True)
@@ -58,6 +73,15 @@ if __name__ == '__main__':
         for m in ('crn', 'ttp'):
             for mm in ('fast', 'exact'):
                 bench((256, 256, 256), model=m, nsteps=10, math=mm)
+        sys.exit(0)
+    if '--aniso' in sys.argv:          # 19-point fibre-tensor operator: tile kernel vs the one-thread-per-node kernel
+        A = (256, 512, 512)
+        bench(A, lap='aniso', nsteps=10)
+        bench(A, lap='aniso', nsteps=10, math='exact')
+        bench(A, lap='aniso', nsteps=10, model=None)
+        bench(A, lap='aniso', nsteps=10, model='mms2v')
+        bench(A, lap='aniso', nsteps=4, kernel='generic')
+        bench(A, lap='aniso', nsteps=4, kernel='generic', math='exact')
         sys.exit(0)
     if '--2d' in sys.argv:             # 2-D grids on the per-step TMA kernel (y-march) and the generic kernel
         for n2 in (4096, 2048, 1024):
