@@ -432,7 +432,7 @@ int pdx_fd_plan_prepare_aniso(pdx_fd_plan* p, const float* DIFF, const float* AV
     a.xb = a.xe = 0;
     CUtensorMap dummy;
     std::memset(&dummy, 0, sizeof(dummy));
-    return launch_fd_aniso_tile(d, a, dummy, p->aniso_maps, nullptr);
+    return launch_fd_aniso_tile(d, a, dummy, p->aniso_maps, nullptr, nullptr);
 }
 
 int pdx_fd_plan_kernel(const pdx_fd_plan* p) { return p ? (p->want_resident ? (int)PDX_KERNEL_RESIDENT : p->kernel) : -1; }
@@ -474,7 +474,10 @@ static int step_once(pdx_fd_plan* p, const float* Uin, float* Uout, float* const
             const CUtensorMap* mU = nullptr;
             if (get_map(p, Uin, &mU)) return 1;
             a.x_chunk = p->aniso_chunk;
-            const int rc = launch_fd_aniso_tile(d, a, *mU, p->aniso_maps, s);
+            const CUtensorMap* mS[PDX_MAX_STATES] = {nullptr, nullptr, nullptr, nullptr};
+            for (int i = 0; i < ns; ++i)
+                if (get_state_map(p, states[i], &mS[i])) return 1;
+            const int rc = launch_fd_aniso_tile(d, a, *mU, p->aniso_maps, mS, s);
             if (!rc) p->launches += 1;
             return rc;
         }

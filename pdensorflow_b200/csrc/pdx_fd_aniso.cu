@@ -8,11 +8,11 @@
 // (same fp32 operations, bit-identical) into six [nx][ny][nz] arrays (aniso_tensor_kernel): a step then reads 6 floats
 // per node instead of 8 channel-last ones, and every component is a plain 3-D array a tensor map can tile.
 //
-// Kernel: the K1 scheme (pdx_fd_tma.cu) with seven staged fields instead of one.  A CTA (8 warps) owns an 8 x 128 tile
+// Kernel: the K1 scheme (pdx_fd_tma.cu) with seven staged fields instead of one.  A CTA owns an 8 x 128 tile
 // of the (y,z) plane and marches along x; U and the six tensor components of a plane arrive as seven
 // cp.async.bulk.tensor boxes of 1 x 10 x 136 floats (halo included, zero filled outside the array) in one slot of a
-// 5-deep shared-memory ring (3 planes in use, 2 in flight; 188 KB, one CTA per SM).  A lane evaluates four consecutive z
-// nodes from 128-bit shared-memory reads:
+// 5-deep shared-memory ring (3 planes in use, 2 in flight; 188 KB + 36 KB of gates, one CTA per SM).  A thread evaluates N = 4 (8 warps
+// per CTA; FAST) or 2 (16 warps; EXACT) consecutive z nodes from 64 / 128-bit shared-memory reads:
 //   flux(axis a, side s) = s 0.5 ( T_a + sum_{b != a} T_b ),
 //   T_a = (C_aa[s e_a] + C_aa[0]) (X[s e_a] - X[0]) / h_a,
 //   T_b = 0.5 (C_ab[s e_a + e_b] + C_ab[s e_a - e_b]) (X[s e_a + e_b] - X[s e_a - e_b]) / h_b,
@@ -21,9 +21,10 @@
 // the oracle; FAST: reciprocal multiplies, FMA contraction).  X is U0 = enforce_boundary(U) (indices clamped to
 // [1, n-2]), the tensor is symmetric padded (indices clamped to the array): both clamps are applied when addressing
 // shared memory, z edges are patched in registers.  The ionic update, the Euler update and the fused halo stores are
-// those of K1; the gates are prefetched one plane ahead in registers.
+// those of K1; the gates arrive by TMA too (boxes without halo, three planes ahead).
 //
 // Algorithmic bytes per node-step with Fenton-Karma: 6 x 4 (tensor) + 32 (U,V,W,S read + written) = 56.
+#include <cstdlib>
 #include "pdx_internal.h"
 #include "pdx_tma.cuh"
 
@@ -34,9 +35,7 @@ namespace {
 constexpr int TZ = 128;
 constexpr int ZH = 4;
 constexpr int COLS = TZ + 2 * ZH;        // 136
-constexpr int NWARP = 8;
-constexpr int NTHREADS = NWARP * 32;
-constexpr int TY = NWARP;
+constexpr int TY = 8;
 constexpr int ROWS = TY + 2;
 constexpr int NF = 7;                    // U, C00, C01, C02, C11, C12, C22
 constexpr int STAGES = 5;
@@ -44,22 +43,45 @@ constexpr int FIELD_FLOATS = (ROWS * COLS * 4 + 127) / 128 * 128 / 4;   // 1376
 constexpr int FIELD_BYTES = FIELD_FLOATS * 4;
 constexpr int SLOT_BYTES = NF * FIELD_BYTES;
 constexpr int TX_BYTES = NF * ROWS * COLS * 4;
-constexpr int BAR_OFF = STAGES * SLOT_BYTES;
-constexpr int SMEM_BYTES = BAR_OFF + STAGES * 8;
+constexpr int SSTAGES = 3;               // gates: planes in flight (a one-plane register prefetch left 22 % of the
+                                         // samples waiting for the loads - ncu r02)
+constexpr int ST_BYTES = TY * TZ * 4;
+constexpr int SRING_OFF = STAGES * SLOT_BYTES;
+constexpr int smem_bytes(int ns) { return SRING_OFF + SSTAGES * ns * ST_BYTES + (STAGES + SSTAGES) * 8; }
 
 enum { F_U = 0, F_C00, F_C01, F_C02, F_C11, F_C12, F_C22 };
 
 struct AnisoMaps {
     CUtensorMap m[NF];
+    CUtensorMap st[PDX_MAX_STATES];      // the gates: boxes of 1 x TY x TZ, no halo
 };
 
-// six values z-1 .. z+4 of a row
-struct W6 {
-    float v[6];
-};
-__device__ __forceinline__ W6 ldw6(const float* row) {      // row points at column z of the shared-memory row
-    const float4 t = *reinterpret_cast<const float4*>(row);
-    return W6{{row[-1], t.x, t.y, t.z, t.w, row[4]}};
+// N consecutive z values of a row / the N + 2 values z-1 .. z+N (N = nodes per thread: 4 or 2)
+template <int N> struct Vn { float v[N]; };
+template <int N> __device__ __forceinline__ Vn<N> ldv_s(const float* p);
+template <> __device__ __forceinline__ Vn<4> ldv_s<4>(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    return Vn<4>{{t.x, t.y, t.z, t.w}};
+}
+template <> __device__ __forceinline__ Vn<2> ldv_s<2>(const float* p) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    return Vn<2>{{t.x, t.y}};
+}
+template <int N> __device__ __forceinline__ void stv_g(float* p, const Vn<N>& a);
+template <> __device__ __forceinline__ void stv_g<4>(float* p, const Vn<4>& a) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+template <> __device__ __forceinline__ void stv_g<2>(float* p, const Vn<2>& a) {
+    *reinterpret_cast<float2*>(p) = make_float2(a.v[0], a.v[1]);
+}
+template <int N> __device__ __forceinline__ Vn<N + 2> ldw(const float* row) {   // row points at column z of the row
+    const Vn<N> t = ldv_s<N>(row);
+    Vn<N + 2> w;
+    w.v[0] = row[-1];
+#pragma unroll
+    for (int e = 0; e < N; ++e) w.v[e + 1] = t.v[e];
+    w.v[N + 1] = row[N];
+    return w;
 }
 
 template <int MATH> __device__ __forceinline__ float mdivh(float x, float h, float rh) {
@@ -79,13 +101,20 @@ __device__ __forceinline__ float t_cross(float cp, float cm, float xp, float xm,
     return mdivh<MATH>(mmul<MATH>(mmul<MATH>(0.5f, madd<MATH>(cp, cm)), msub<MATH>(xp, xm)), h, rh);
 }
 
-template <int MODEL, int MATH>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// N nodes per thread: 4 (8 warps per CTA, 128-bit accesses) or 2 (16 warps, 64-bit accesses: a tenth more instructions
+// per node, twice the warps to hide the shared-memory and issue latencies of a one-CTA-per-SM kernel)
+template <int MODEL, int MATH, int N>
+__global__ void __launch_bounds__(TY * TZ / N, 1)
 fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ FdArgs a) {
     constexpr int NS = NStates<MODEL>::value;
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* sring = smem + SRING_OFF;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sring + SSTAGES * NS * ST_BYTES);
+    uint64_t* sfull = full + STAGES;
+    constexpr int TPR = TZ / N;                      // threads per tile row
+    typedef Vn<N> V;
+    typedef Vn<N + 2> W;
+    const int tid = threadIdx.x, zl = tid % TPR, trow = tid / TPR;
 
     int b = blockIdx.x;
     const int tz = b % a.ntz;  b /= a.ntz;
@@ -108,22 +137,34 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
         for (int f = 1; f < NF; ++f) tma_load_3d(slot(j, f), &maps.m[f], z0 - ZH, y0 - 1, qc, bar);
     };
     auto wait_plane = [&](int j) { mbar_wait(&full[j % STAGES], (uint32_t)((j / STAGES) & 1)); };
+    auto sslot = [&](int i, int s) { return reinterpret_cast<float*>(sring + ((i % SSTAGES) * (NS > 0 ? NS : 1) + s) * ST_BYTES); };
+    auto issue_states = [&](int i) {   // thread 0 only; plane xb + i
+        uint64_t* bar = &sfull[i % SSTAGES];
+        mbar_expect_tx(bar, NS * ST_BYTES);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) tma_load_3d(sslot(i, s), &maps.st[s], z0, y0, xb + i, bar);
+    };
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+#pragma unroll
+        for (int s = 0; s < SSTAGES; ++s) mbar_init(&sfull[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
     if (tid == 0) {
         const int n0 = min(STAGES, nlog);
-        for (int j = 0; j < n0; ++j) issue(j);
+        for (int j = 0; j < n0; ++j) {
+            issue(j);
+            if (NS > 0 && j < SSTAGES && j < np) issue_states(j);
+        }
     }
 
     // ---- per-thread geometry (constant along the march) ----
-    const int  z   = z0 + 4 * lane;
-    const int  col = ZH + 4 * lane;
-    const int  gy  = y0 + warp;
+    const int  z   = z0 + N * zl;
+    const int  col = ZH + N * zl;
+    const int  gy  = y0 + trow;
     const bool act = z < a.nz && gy < a.ny;
     const int  g   = min(gy, a.ny - 1);
     // X = U0: rows clamped to [yclo, ychi]; tensor: rows clamped to the array
@@ -134,46 +175,42 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
     const int cm = (max(g - 1, 0) - (y0 - 1)) * COLS + col;
     const int cp = (min(g + 1, a.ny - 1) - (y0 - 1)) * COLS + col;
     const bool zb_tile = (z0 - 1 < a.zclo) || (z0 + TZ > a.zchi);        // CTA uniform
-    const bool yb_tile = (y0 - 1 < a.yclo) || (y0 + TY > a.ychi);
-    const bool xlo2 = z < a.zclo, xlo1 = z - 1 < a.zclo, xhi2 = z + 3 > a.zchi, xhi1 = z + 4 > a.zchi;
-    const bool clo1 = z - 1 < 0, chi1 = z + 4 > a.nz - 1;
+    const bool xlo2 = z < a.zclo, xlo1 = z - 1 < a.zclo, xhi2 = z + N - 1 > a.zchi, xhi1 = z + N > a.zchi;
+    const bool clo1 = z - 1 < 0, chi1 = z + N > a.nz - 1;
+    // the ionic update takes the raw potential: the centre row at its unclamped index, unless the PLANE was clamped
+    const bool row_clamped = g < a.yclo || g > a.ychi;
     // z-edge patches: X clamps to [zclo, zchi], the tensor to [0, nz-1]
-    auto fixX6 = [&](W6& w) {
+    auto fixXw = [&](W& w) {
         if (xlo2) w.v[1] = w.v[2];
-        if (xhi2) w.v[4] = w.v[3];
+        if (xhi2) w.v[N] = w.v[N - 1];
         if (xlo1) w.v[0] = w.v[1];
-        if (xhi1) w.v[5] = w.v[4];
+        if (xhi1) w.v[N + 1] = w.v[N];
     };
-    auto fixX4 = [&](F4& w) {
+    auto fixXv = [&](V& w) {
         if (xlo2) w.v[0] = w.v[1];
-        if (xhi2) w.v[3] = w.v[2];
+        if (xhi2) w.v[N - 1] = w.v[N - 2];
     };
-    auto fixC6 = [&](W6& w) {
+    auto fixCw = [&](W& w) {
         if (clo1) w.v[0] = w.v[1];
-        if (chi1) w.v[5] = w.v[4];
+        if (chi1) w.v[N + 1] = w.v[N];
     };
 
     const float hx = a.hx, hy = a.hy, hz = a.hz;
     const float rhx = 1.0f / hx, rhy = 1.0f / hy, rhz = 1.0f / hz;      // FAST only
 
-    F4 stn[NS > 0 ? NS : 1];
-    auto load_states = [&](int p) {
-        if (!act) return;
-        const size_t gi = ((size_t)p * a.ny + gy) * a.nz + z;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) stn[s] = ldg4(a.st[s] + gi);
-    };
-    if (NS > 0 && np > 0) load_states(xb);
+    const int srow = trow * TZ + N * zl;
 
     for (int i = 0; i < np; ++i) {
         const int p = xb + i;
         const int jc = i + 1;
         if (i == 0) { wait_plane(0); wait_plane(1); }
         wait_plane(i + 2);
-        F4 stc[NS > 0 ? NS : 1];
+        V stc[NS > 0 ? NS : 1];
+        if (NS > 0) {
+            mbar_wait(&sfull[i % SSTAGES], (uint32_t)((i / SSTAGES) & 1));
 #pragma unroll
-        for (int s = 0; s < NS; ++s) stc[s] = stn[s];
-        if (NS > 0 && i + 1 < np) load_states(p + 1);
+            for (int s = 0; s < NS; ++s) stc[s] = ldv_s<N>(sslot(i, s) + srow);
+        }
 
         if (act) {
             const size_t gi = ((size_t)p * a.ny + gy) * a.nz + z;
@@ -181,29 +218,33 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
             const float* Uc = slot(jc, F_U);
             const float* Up = slot(jc + 1, F_U);
             // ---- potential ----
-            W6 x_mc = ldw6(Um + rc), x_pc = ldw6(Up + rc);                 // planes i-1 / i+1, row j
-            W6 x_cm = ldw6(Uc + rm), x_cc = ldw6(Uc + rc), x_cp = ldw6(Uc + rp);   // plane i, rows j-1, j, j+1
-            F4 x_mm = lds4(Um + rm), x_mp = lds4(Um + rp), x_pm = lds4(Up + rm), x_pp = lds4(Up + rp);
-            F4 raw = F4{{x_cc.v[1], x_cc.v[2], x_cc.v[3], x_cc.v[4]}};
-            const bool bnd = yb_tile || zb_tile || p < a.xclo || p > a.xchi;     // CTA uniform
-            if (bnd && MODEL != PDX_MODEL_NONE) raw = ldg4(a.Uin + gi);
+            W x_mc = ldw<N>(Um + rc), x_pc = ldw<N>(Up + rc);                        // planes i-1 / i+1, row j
+            W x_cm = ldw<N>(Uc + rm), x_cc = ldw<N>(Uc + rc), x_cp = ldw<N>(Uc + rp);   // plane i, rows j-1, j, j+1
+            V x_mm = ldv_s<N>(Um + rm), x_mp = ldv_s<N>(Um + rp), x_pm = ldv_s<N>(Up + rm), x_pp = ldv_s<N>(Up + rp);
+            V raw;
+#pragma unroll
+            for (int e = 0; e < N; ++e) raw.v[e] = x_cc.v[e + 1];
+            if (MODEL != PDX_MODEL_NONE) {
+                if (p < a.xclo || p > a.xchi) raw = ldv_s<N>(a.Uin + gi);     // CTA uniform, two planes of the grid
+                else if (row_clamped) raw = ldv_s<N>(Uc + cc);                // rows 0 and ny-1: the halo row of the tile
+            }
             if (zb_tile) {
-                fixX6(x_mc); fixX6(x_pc); fixX6(x_cm); fixX6(x_cc); fixX6(x_cp);
-                fixX4(x_mm); fixX4(x_mp); fixX4(x_pm); fixX4(x_pp);
+                fixXw(x_mc); fixXw(x_pc); fixXw(x_cm); fixXw(x_cc); fixXw(x_cp);
+                fixXv(x_mm); fixXv(x_mp); fixXv(x_pm); fixXv(x_pp);
             }
             // ---- tensor ----
-            const F4 c00m = lds4(slot(jc - 1, F_C00) + cc), c00c = lds4(slot(jc, F_C00) + cc), c00p = lds4(slot(jc + 1, F_C00) + cc);
-            const F4 c11m = lds4(slot(jc, F_C11) + cm), c11c = lds4(slot(jc, F_C11) + cc), c11p = lds4(slot(jc, F_C11) + cp);
-            W6 c22 = ldw6(slot(jc, F_C22) + cc);
-            const F4 c01mm = lds4(slot(jc - 1, F_C01) + cm), c01mp = lds4(slot(jc - 1, F_C01) + cp);
-            const F4 c01pm = lds4(slot(jc + 1, F_C01) + cm), c01pp = lds4(slot(jc + 1, F_C01) + cp);
-            W6 c02m = ldw6(slot(jc - 1, F_C02) + cc), c02p = ldw6(slot(jc + 1, F_C02) + cc);
-            W6 c12m = ldw6(slot(jc, F_C12) + cm), c12p = ldw6(slot(jc, F_C12) + cp);
-            if (zb_tile) { fixC6(c22); fixC6(c02m); fixC6(c02p); fixC6(c12m); fixC6(c12p); }
+            const V c00m = ldv_s<N>(slot(jc - 1, F_C00) + cc), c00c = ldv_s<N>(slot(jc, F_C00) + cc), c00p = ldv_s<N>(slot(jc + 1, F_C00) + cc);
+            const V c11m = ldv_s<N>(slot(jc, F_C11) + cm), c11c = ldv_s<N>(slot(jc, F_C11) + cc), c11p = ldv_s<N>(slot(jc, F_C11) + cp);
+            W c22 = ldw<N>(slot(jc, F_C22) + cc);
+            const V c01mm = ldv_s<N>(slot(jc - 1, F_C01) + cm), c01mp = ldv_s<N>(slot(jc - 1, F_C01) + cp);
+            const V c01pm = ldv_s<N>(slot(jc + 1, F_C01) + cm), c01pp = ldv_s<N>(slot(jc + 1, F_C01) + cp);
+            W c02m = ldw<N>(slot(jc - 1, F_C02) + cc), c02p = ldw<N>(slot(jc + 1, F_C02) + cc);
+            W c12m = ldw<N>(slot(jc, F_C12) + cm), c12p = ldw<N>(slot(jc, F_C12) + cp);
+            if (zb_tile) { fixCw(c22); fixCw(c02m); fixCw(c02p); fixCw(c12m); fixCw(c12p); }
 
-            F4 out;
+            V out;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < N; ++e) {
                 const int k0 = e, k1 = e + 1, k2 = e + 2;          // window indices of z-1, z, z+1
                 const float x0 = x_cc.v[k1];
                 // axis x, side +/-: normal, transverse y, transverse z     (:50-62)
@@ -244,14 +285,17 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
                 }
                 out.v[e] = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
             }
-            stg4(a.Uout + gi, out);
-            if (a.mirror_lo && p == a.mirror_lo_plane) stg4(a.mirror_lo + (size_t)gy * a.nz + z, out);
-            if (a.mirror_hi && p == a.mirror_hi_plane) stg4(a.mirror_hi + (size_t)gy * a.nz + z, out);
+            stv_g<N>(a.Uout + gi, out);
+            if (a.mirror_lo && p == a.mirror_lo_plane) stv_g<N>(a.mirror_lo + (size_t)gy * a.nz + z, out);
+            if (a.mirror_hi && p == a.mirror_hi_plane) stv_g<N>(a.mirror_hi + (size_t)gy * a.nz + z, out);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) stg4(a.st[s] + gi, stc[s]);
+            for (int s = 0; s < NS; ++s) stv_g<N>(a.st[s] + gi, stc[s]);
         }
         __syncthreads();                              // everyone is done with logical plane i
-        if (tid == 0 && i + STAGES < nlog) issue(i + STAGES);
+        if (tid == 0) {
+            if (i + STAGES < nlog) issue(i + STAGES);
+            if (NS > 0 && i + SSTAGES < np) issue_states(i + SSTAGES);
+        }
     }
 }
 
@@ -272,14 +316,14 @@ __global__ void __launch_bounds__(256) aniso_tensor_kernel(const float* __restri
     }
 }
 
-template <int MODEL, int MATH>
+template <int MODEL, int MATH, int N>
 int launch_inst(const FdArgs& a0, const AnisoMaps& m, cudaStream_t s) {
-    auto kern = fd_aniso_kernel<MODEL, MATH>;
+    auto kern = fd_aniso_kernel<MODEL, MATH, N>;
     static bool attr_done[PDX_MAX_DEVICES] = {};
     int dev = 0;
     if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
     if (dev < 0 || dev >= PDX_MAX_DEVICES || !attr_done[dev]) {
-        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(NStates<MODEL>::value)),
                        "cudaFuncSetAttribute(smem, aniso)"))
             return 1;
         if (dev >= 0 && dev < PDX_MAX_DEVICES) attr_done[dev] = true;
@@ -290,14 +334,20 @@ int launch_inst(const FdArgs& a0, const AnisoMaps& m, cudaStream_t s) {
     a.nchunk = (nplanes + a.x_chunk - 1) / a.x_chunk;
     const long long nb = (long long)a.ntz * a.nty * a.nchunk;
     if (nb > 0x7fffffffLL) { set_error("fd_aniso: grid too large"); return 1; }
-    kern<<<(unsigned)nb, NTHREADS, SMEM_BYTES, s>>>(m, a);
+    kern<<<(unsigned)nb, TY * TZ / N, smem_bytes(NStates<MODEL>::value), s>>>(m, a);
     count_launch();
     return check_cuda(cudaGetLastError(), "fd_aniso_kernel launch");
 }
 
 template <int MODEL>
 int launch_math(int math, const FdArgs& a, const AnisoMaps& m, cudaStream_t s) {
-    return math == PDX_MATH_EXACT ? launch_inst<MODEL, PDX_MATH_EXACT>(a, m, s) : launch_inst<MODEL, PDX_MATH_FAST>(a, m, s);
+    // nodes per thread (PDX_ANISO_NPT=4|2 overrides).  Measured on 256 x 512^2 FK (profiles/r02_aniso_throughput.jsonl):
+    // FAST 85.4 Gnode-steps/s with 4 against 84.1 with 2 (heat 124 / 113); EXACT (IEEE divisions: issue bound) 8.3
+    // against 13.4 - more warps pay only there.
+    static const int npt_env = [] { const char* e = getenv("PDX_ANISO_NPT"); return e ? atoi(e) : 0; }();
+    if (math == PDX_MATH_EXACT)
+        return npt_env == 4 ? launch_inst<MODEL, PDX_MATH_EXACT, 4>(a, m, s) : launch_inst<MODEL, PDX_MATH_EXACT, 2>(a, m, s);
+    return npt_env == 2 ? launch_inst<MODEL, PDX_MATH_FAST, 2>(a, m, s) : launch_inst<MODEL, PDX_MATH_FAST, 4>(a, m, s);
 }
 
 }  // namespace
@@ -328,10 +378,11 @@ int launch_aniso_tensor(const float* DIFF, const float* AVEC, float* C, int64_t 
 }
 
 int launch_fd_aniso_tile(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mapU, const CUtensorMap* mapC,
-                         cudaStream_t s) {
+                         const CUtensorMap* const* mapS, cudaStream_t s) {
     AnisoMaps m;
     m.m[F_U] = mapU;
     for (int f = 1; f < NF; ++f) m.m[f] = mapC[f - 1];
+    for (int i = 0; i < PDX_MAX_STATES; ++i) m.st[i] = (mapS && mapS[i]) ? *mapS[i] : mapU;
     switch (d.model) {
         case PDX_MODEL_NONE:     return launch_math<PDX_MODEL_NONE>(d.math_mode, a, m, s);
         case PDX_MODEL_FENTON4V: return launch_math<PDX_MODEL_FENTON4V>(d.math_mode, a, m, s);

@@ -101,7 +101,7 @@ bool fd_aniso_tile_supported(const pdx_fd_desc& d);
 int  fd_aniso_auto_chunk(const pdx_fd_desc& d);
 int  launch_aniso_tensor(const float* DIFF, const float* AVEC, float* C, int64_t n, cudaStream_t s);
 int  launch_fd_aniso_tile(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mapU, const CUtensorMap* mapC /* 6 */,
-                          cudaStream_t s);
+                          const CUtensorMap* const* mapS /* per state, box = fd_tma_state_box */, cudaStream_t s);
 
 // SM-resident multi-step kernel for 2-D grids (pdx_fd_resident.cu)
 #define PDX_RESIDENT_FLAG_STRIDE 32

@@ -19,6 +19,19 @@ except Exception:
 BYTES = {'fenton4v': 32, 'mms2v': 16, 'ms2v': 16, None: 8, 'crn': 8 + 19 * 8, 'ttp': 8 + 18 * 8 + 4 * 4}
 
 
+def aniso_fields(shape, diff):
+    """sigma_t = diff/4, sigma_l = diff, fibres rotating in the (x,y) plane with z: a full tensor at every node."""
+    DIFF = torch.empty(tuple(shape) + (2,), device='cuda')
+    DIFF[..., 0] = 0.25 * diff
+    DIFF[..., 1] = 0.75 * diff
+    ang = torch.linspace(0.0, 3.0, shape[2], device='cuda').view(1, 1, -1).expand(*shape)
+    a = torch.stack([torch.cos(ang), torch.sin(ang), 0.3 * torch.ones_like(ang)], dim=-1)
+    a = a / a.norm(dim=-1, keepdim=True)
+    AVEC = torch.stack([a[..., 0] * a[..., 0], a[..., 0] * a[..., 1], a[..., 0] * a[..., 2], a[..., 1] * a[..., 1],
+                        a[..., 1] * a[..., 2], a[..., 2] * a[..., 2]], dim=-1).contiguous()
+    return DIFF, AVEC
+
+
 def bench(shape, model='fenton4v', math='fast', kernel='auto', lap='homog', nsteps=40, reps=3, dt=0.1, diff=0.8):
     name = model
     mobj = model
@@ -30,16 +43,7 @@ def bench(shape, model='fenton4v', math='fast', kernel='auto', lap='homog', nste
     DIFF = torch.full(shape, diff, device='cuda') if lap == 'heterog' else None
     AVEC = None
     if lap == 'aniso':
-        # sigma_t = diff/4, sigma_l = diff, fibres rotating in the (x,y) plane with z: a full tensor at every node
-        DIFF = torch.empty(tuple(shape) + (2,), device='cuda')
-        DIFF[..., 0] = 0.25 * diff
-        DIFF[..., 1] = 0.75 * diff
-        ang = torch.linspace(0.0, 3.0, shape[2], device='cuda').view(1, 1, -1).expand(*shape)
-        a = torch.stack([torch.cos(ang), torch.sin(ang), 0.3 * torch.ones_like(ang)], dim=-1)
-        a = a / a.norm(dim=-1, keepdim=True)
-        AVEC = torch.stack([a[..., 0] * a[..., 0], a[..., 0] * a[..., 1], a[..., 0] * a[..., 2], a[..., 1] * a[..., 1],
-                            a[..., 1] * a[..., 2], a[..., 2] * a[..., 2]], dim=-1).contiguous()
-        del ang, a
+        DIFF, AVEC = aniso_fields(shape, diff)
     st = FDStepper(shape, (1.0,) * len(shape), dt, diff, model=mobj, math=math, kernel=kernel, lap=lap, DIFF=DIFF, AVEC=AVEC)
     U = st.U()
     U.fill_(u_rest)

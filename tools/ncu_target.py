@@ -31,8 +31,13 @@ def main():
     else:
         dt = 0.1
     DIFF = torch.full(shape, 0.8, device='cuda') if args.lap == 'heterog' else None
+    AVEC = None
+    if args.lap == 'aniso':
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from bench_variants import aniso_fields
+        DIFF, AVEC = aniso_fields(shape, 0.8)
     st = FDStepper(shape, (1.0,) * len(shape), dt, 0.8, model=model, math=args.math, kernel=args.kernel, lap=args.lap,
-                   DIFF=DIFF, x_chunk=args.x_chunk)
+                   DIFF=DIFF, AVEC=AVEC, x_chunk=args.x_chunk)
     U = st.U(); U.fill_(-80.0); U[0:2] = 20.0
     for _ in range(args.steps):
         st.step(1)
