@@ -295,6 +295,20 @@ int pdx_fem_explicit_step_sell(int model, int math_mode, const float* params, in
                                const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
                                int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, void* stream);
 
+/* The partitioned step (sell = 0: CSR as _part, 1: SELL-32 as _sell) ordered by NEIGHBOUR FLAGS instead of a barrier
+ * between steps.  ctrl: this rank's control block, uint32[8] in memory the neighbours can write (NVLink peer /
+ * symmetric memory), zeroed once before the first step with every rank's initial U in place; ctrl_lo / ctrl_hi: the
+ * neighbours' blocks (NULL at the ends of the chain).  Only the CTAs that hold the first send_lo / last send_hi rows
+ * take part (they read the ghost rows and store into the neighbour): they wait until that neighbour has published as
+ * many steps as this rank (its ghost rows are in U_in, and it no longer reads the buffer this step overwrites), and
+ * the last of them publishes the step into the neighbour's block.  One GPU per rank (or all ranks on one stream): the
+ * waiting CTAs occupy their SMs. */
+int pdx_fem_explicit_step_sync(int sell, int model, int math_mode, const float* params, int32_t n_local, int32_t row_lo,
+                               const int32_t* rowptr, const int32_t* col, const float* kval, const float* mlinv,
+                               const float* U_in, float* U_out, float* const* states, const float* I0, float dt,
+                               int32_t send_lo, float* mirror_lo, int32_t send_hi, float* mirror_hi, uint32_t* ctrl,
+                               uint32_t* ctrl_lo, uint32_t* ctrl_hi, void* stream);
+
 /* ------------------------------------------------------------------ FEM path across GPUs */
 /* Row-block partitioned Jacobi-PCG = the semi-implicit step of MonodomainSolver / HeatSolver
  * (monodomainSolver.py:98-108, heatSolver.py:127-135, conjgrad.py:172-203,257-312) with the mesh nodes

@@ -102,6 +102,8 @@ _SIGNATURES = {
                                              _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
     'pdx_fem_explicit_step_sell': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
                                              _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
+    'pdx_fem_explicit_step_sync': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
+                                             _P, C.POINTER(_P), _P, C.c_float, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     'pdx_fem_assemble': (C.c_int, [C.c_int, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'pdx_round_to_f32': (C.c_int, [_P, _P, C.c_int64, _P]),
     'pdx_sell_slice_widths': (C.c_int, [C.c_int32, _P, _P, _P]),

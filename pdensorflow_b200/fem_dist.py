@@ -200,7 +200,7 @@ class PartitionedExplicitFEM:
     """
 
     def __init__(self, n_global, rowptr, col, kval, mlump, dt, model='fenton4v', params=None, rank=0, world=1,
-                 group=None, math='fast', device=None, layout='sell', connect=True, exchange='auto'):
+                 group=None, math='fast', device=None, layout='sell', connect=True, exchange='auto', sync='auto'):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != 'cuda':
             raise L.PdxError('PartitionedExplicitFEM needs a CUDA device: there is no CPU path')
@@ -220,6 +220,13 @@ class PartitionedExplicitFEM:
         if exchange not in ('auto', 'band', 'lists'):
             raise ValueError("exchange must be 'auto', 'band' or 'lists'")
         self.exchange = exchange
+        # sync: 'flags' = the step kernels order themselves through neighbour flags in peer memory
+        # (pdx_fem_explicit_step_sync, band exchange only); 'barrier' = one symmetric-memory barrier per step;
+        # 'auto' = flags whenever the exchange is the band form
+        if sync not in ('auto', 'flags', 'barrier'):
+            raise ValueError("sync must be 'auto', 'flags' or 'barrier'")
+        self.sync = sync
+        self._ctrl = self._ctrl_lo = self._ctrl_hi = None
         self._push = None
         self._local = world > 1 and not connect      # ranks sharing one GPU in one process: see connect_local
         if world > 1 and connect:
@@ -263,6 +270,22 @@ class PartitionedExplicitFEM:
             self._peer_lo = self._peer_hi = [None, None]
         for b in self.U:
             b.fill_(-80.0 if self.model_id != L.MODEL_NONE else 0.0)
+        if self._hdl is not None and self.exchange == 'band' and self.sync in ('auto', 'flags'):
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            self._ctrl = symm.empty((32,), dtype=torch.int32, device=dev)
+            self._ctrl.zero_()
+            h = symm.rendezvous(self._ctrl, group if group is not None else dist.group.WORLD)
+            self._ctrl_hdl = h
+            self._ctrl_lo = h.buffer_ptrs[rank - 1] if rank > 0 else None
+            self._ctrl_hi = h.buffer_ptrs[rank + 1] if rank < world - 1 else None
+            self.sync = 'flags'
+        elif self.sync == 'flags' and not self._local:
+            if world > 1:
+                raise ValueError("sync='flags' needs the band exchange")
+            self.sync = 'barrier'
+        elif self.sync == 'auto' and not self._local:
+            self.sync = 'barrier'
         if self._hdl is not None and self.exchange == 'lists':
             self._install_push([[int(q) for q in h.buffer_ptrs] for h in self._hdl])
         self._cur = 0
@@ -312,6 +335,18 @@ class PartitionedExplicitFEM:
             if f.exchange == 'lists':
                 f._peer_lo = f._peer_hi = [None, None]
                 f._install_push([[g.U[b].data_ptr() for g in ranks] for b in range(2)])
+        if all(f.exchange == 'band' and f.sync in ('auto', 'flags') for f in ranks):
+            # the neighbour-flag protocol on one GPU: the ranks share a stream, so a waiting kernel's neighbours have
+            # always finished already - the flags are exercised, never contended
+            for f in ranks:
+                f._ctrl = torch.zeros(32, dtype=torch.int32, device=f.device)
+            for f in ranks:
+                f.sync = 'flags'
+                f._ctrl_lo = ranks[f.rank - 1]._ctrl.data_ptr() if f.rank > 0 else None
+                f._ctrl_hi = ranks[f.rank + 1]._ctrl.data_ptr() if f.rank < f.world - 1 else None
+        else:
+            for f in ranks:
+                f.sync = 'barrier'
 
     @staticmethod
     def step_local(ranks, nsteps=1):
@@ -323,6 +358,9 @@ class PartitionedExplicitFEM:
     def set_global_U(self, U):
         """Install a global potential (host array): own rows and ghost columns become valid."""
         t = torch.from_numpy(np.ascontiguousarray(U, dtype=np.float32).reshape(-1)).to(self.device)
+        if self._ctrl is not None and not self._local and self._primed:
+            # neighbour flags: a neighbour's last step may still be storing ghost rows into this rank's buffers
+            self._hdl[0].barrier(channel=0)
         self.U[self._cur].copy_(t)
         self._primed = self.world == 1 or self._local
 
@@ -343,8 +381,18 @@ class PartitionedExplicitFEM:
         lib = L.lib()
         dt32 = float(np.float32(self.dt))
         fn = lib.pdx_fem_explicit_step_sell if self.layout == 'sell' else lib.pdx_fem_explicit_step_part
+        flags = self._ctrl is not None
         for _ in range(nsteps):
             i, o = self._cur, self._cur ^ 1
+            if flags:
+                L.check(lib.pdx_fem_explicit_step_sync(
+                    1 if self.layout == 'sell' else 0, self.model_id, self.math_id, self._params, self.nloc, self.lo,
+                    L.ptr(self.rowptr), L.ptr(self.col), L.ptr(self.kval), L.ptr(self.mlinv), L.ptr(self.U[i]),
+                    L.ptr(self.U[o]), self._states_arr, L.ptr(I0), dt32, self.send_lo, C.c_void_p(self._peer_lo[o]),
+                    self.send_hi, C.c_void_p(self._peer_hi[o]), L.ptr(self._ctrl), C.c_void_p(self._ctrl_lo),
+                    C.c_void_p(self._ctrl_hi), L.stream_ptr()))
+                self._cur = o
+                continue
             L.check(fn(
                 self.model_id, self.math_id, self._params, self.nloc, self.lo, L.ptr(self.rowptr), L.ptr(self.col),
                 L.ptr(self.kval), L.ptr(self.mlinv), L.ptr(self.U[i]), L.ptr(self.U[o]), self._states_arr, L.ptr(I0),
@@ -358,6 +406,38 @@ class PartitionedExplicitFEM:
                 self._hdl[0].barrier(channel=0)
             self._cur = o
         self.nsteps_done += nsteps
+
+    def run(self, nsteps, block=10, I0=None):
+        """nsteps steps as CUDA-graph replays of ``block`` steps (+ a remainder through step()).  The neighbour-flag
+        protocol lives on the device (the kernels count their own steps), so a captured block replays correctly;
+        with sync='barrier' on several GPUs the per-step barrier keeps the steps un-captured."""
+        if self.world > 1 and not self._local and self._ctrl is None:
+            return self.step(nsteps, I0)
+        if self._push is not None and self._push[3] and self.world > 1 and not self._local:
+            return self.step(nsteps, I0)
+        if not self._primed:
+            self._prime()
+        block = max(2, block - block % 2)
+        nblk, rem = divmod(nsteps, block)
+        if nblk:
+            key = (block, self._cur, None if I0 is None else I0.data_ptr())
+            graphs = self.__dict__.setdefault('_graphs', {})
+            if key not in graphs:
+                g = torch.cuda.CUDAGraph()
+                st = torch.cuda.Stream(device=self.device)
+                st.wait_stream(torch.cuda.current_stream(self.device))
+                done0, cur0 = self.nsteps_done, self._cur
+                with torch.cuda.stream(st):
+                    with torch.cuda.graph(g, stream=st):
+                        self.step(block, I0)
+                torch.cuda.current_stream(self.device).wait_stream(st)
+                self.nsteps_done, self._cur = done0, cur0          # capturing executes nothing
+                graphs[key] = g
+            for _ in range(nblk):
+                graphs[key].replay()
+            self.nsteps_done += nblk * block
+        if rem:
+            self.step(rem, I0)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -45,6 +45,14 @@ def test_single_rank_matches_oracle(cuda):
         assert rel_l2(got, Uo) <= tol, (math, rel_l2(got, Uo))
 
 
+def fem_gather(fem, dist, world):
+    """The global potential assembled from every rank's owned rows (host array)."""
+    torch.cuda.synchronize()
+    parts = [None] * world
+    dist.all_gather_object(parts, (fem.lo, fem.owned_U().cpu().numpy()))
+    return np.concatenate([p for _, p in sorted(parts, key=lambda t: t[0])])
+
+
 def _worker(rank, world, port, nsteps, q):
     import torch.distributed as dist
     from pdensorflow_b200.fem_dist import PartitionedExplicitFEM, row_blocks
@@ -60,13 +68,36 @@ def _worker(rank, world, port, nsteps, q):
         rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA, lo, hi)
         fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=rank, world=world)
         assert (fem.send_lo > 0) == (rank > 0) and (fem.send_hi > 0) == (rank < world - 1)
+        assert fem.sync == 'flags'          # band exchange: the step kernels order themselves through neighbour flags
         fem.set_global_U(_initial(n, DIMS))
-        fem.step(nsteps)
+        fem.step(nsteps // 2)
+        fem.set_global_U(fem_gather(fem, dist, world))      # re-install mid-run: flags keep counting across it
+        fem.run(nsteps - nsteps // 2, block=6)              # graph replays of 6 steps + a remainder of 2
         torch.cuda.synchronize()
         q.put((rank, lo, fem.owned_U().cpu().numpy(), fem.states[0].cpu().numpy()))
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def test_graph_replayed_blocks_equal_single_steps(cuda):
+    from pdensorflow_b200.fem_dist import PartitionedExplicitFEM
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    nx, ny, nz = DIMS
+    n = nx * ny * nz
+    rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA)
+    out = []
+    for how in ('step', 'run'):
+        fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact')
+        fem.set_global_U(_initial(n, DIMS))
+        if how == 'step':
+            fem.step(27)
+        else:
+            fem.run(27, block=6)
+        torch.cuda.synchronize()
+        assert fem.nsteps_done == 27
+        out.append((fem.current_U().cpu().numpy(), fem.states[2].cpu().numpy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
 @pytest.mark.parametrize('world', [2, 3])
@@ -105,8 +136,9 @@ def test_partitioned_ranks_match_single_rank_bitwise(cuda, world):
         assert np.array_equal(V, Vref[lo:lo + V.shape[0]])
 
 
+@pytest.mark.parametrize('sync', ['flags', 'barrier'])
 @pytest.mark.parametrize('world,layout', [(2, 'sell'), (3, 'sell'), (3, 'csr')])
-def test_ranks_sharing_one_gpu_match_single_rank_bitwise(cuda, world, layout):
+def test_ranks_sharing_one_gpu_match_single_rank_bitwise(cuda, world, layout, sync):
     """The ghost stores fused into the explicit step kernel on a ONE-GPU box: the row blocks live in one process and
     store their edge rows into each other's buffers through plain device pointers (PartitionedExplicitFEM.connect_local)."""
     from pdensorflow_b200.fem_dist import PartitionedExplicitFEM, row_blocks
@@ -118,9 +150,10 @@ def test_ranks_sharing_one_gpu_match_single_rank_bitwise(cuda, world, layout):
     for r, (lo, hi) in enumerate(row_blocks(n, world)):
         rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA, lo, hi)
         ranks.append(PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=r, world=world,
-                                            layout=layout, connect=False))
+                                            layout=layout, connect=False, sync=sync))
     PartitionedExplicitFEM.connect_local(ranks)
     for f in ranks:
+        assert f.sync == sync
         assert (f.send_lo > 0) == (f.rank > 0) and (f.send_hi > 0) == (f.rank < world - 1)
         f.set_global_U(_initial(n, DIMS))
     PartitionedExplicitFEM.step_local(ranks, nsteps)

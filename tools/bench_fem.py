@@ -22,6 +22,8 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--skip-config1', action='store_true')
     ap.add_argument('--layout', default='sell', choices=['sell', 'csr'])
+    ap.add_argument('--sync', default='auto', choices=['auto', 'flags', 'barrier'])
+    ap.add_argument('--no-graph', action='store_true', help='one Python launch per step instead of graph replays of 10 steps')
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -37,7 +39,7 @@ def main():
     rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, (0.25, 0.25, 0.25), 1e-3, lo, hi)
     setup = time.time() - t0
     fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, 0.1, model='fenton4v', math='fast', rank=rank, world=world,
-                                 layout=args.layout)
+                                 layout=args.layout, sync=args.sync)
     U = fem.current_U()
     U.fill_(-80.0)
     U[: 2 * ny * nz] = 20.0
@@ -46,8 +48,13 @@ def main():
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    advance = fem.step if args.no_graph else fem.run
+    advance(20)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0.record()
-    fem.step(args.steps)
+    advance(args.steps)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
@@ -63,7 +70,7 @@ def main():
                           'n_gpus': world, 'ms_per_step': round(ms, 4), 'gnode_steps_per_s': round(n / ms / 1e6, 2),
                           'nnz_per_row': round(rbar, 2), 'algorithmic_bytes_per_node_step': round(bpn, 1),
                           'algorithmic_gbs_per_gpu': round(n / world * bpn / ms / 1e6, 1), 'setup_s_per_rank': round(setup, 1),
-                          'ghost_rows_sent': [fem.send_lo, fem.send_hi], 'finite': ok, 'layout': args.layout,
+                          'ghost_rows_sent': [fem.send_lo, fem.send_hi], 'sync': fem.sync, 'graph_blocks': not args.no_graph, 'finite': ok, 'layout': args.layout,
                           'parity': 'UNPINNED: the explicit lumped step has no reference implementation (SURVEY 8a row E); '
                                     'checked against the oracle restatement only (tests/test_fem_dist_gpu.py)',
                           'sell_padding': round(getattr(fem, 'padding', 1.0), 4)}), flush=True)
