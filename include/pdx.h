@@ -100,6 +100,11 @@ typedef struct pdx_fd_desc {
     float   dirichlet_value;
     int32_t x_chunk;         /* planes marched per CTA by the TMA kernel; 0 = auto */
     float   params[PDX_MAX_PARAMS];
+    int32_t pitch_z;         /* floats between consecutive rows of EVERY array of the plan (U, states, DIFF); 0 = nz
+                                (contiguous, the reference's layout).  The tile kernel needs rows that are 16-byte
+                                multiples: a grid with nz % 4 != 0 runs on it when the caller keeps its arrays with
+                                pitch_z = nz rounded up to a multiple of 4 (pdensorflow_b200.fd.FDStepper does); the
+                                pad columns are scratch.  Closed-form models, 2-D / 3-D, not the SM-resident kernel. */
 } pdx_fd_desc;
 
 typedef struct pdx_fd_plan pdx_fd_plan;

@@ -32,6 +32,7 @@ class FdDesc(C.Structure):
         ('dirichlet', C.c_int32), ('dirichlet_value', C.c_float),
         ('x_chunk', C.c_int32),
         ('params', C.c_float * MAX_PARAMS),
+        ('pitch_z', C.c_int32),
     ]
 
 

@@ -89,10 +89,11 @@ static CUresult encode_tiled(CUtensorMap* map, void* base, const cuuint64_t* gdi
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-int make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int nz, int box_x, int box_y,
+int make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int nz, int pitch_z, int box_x, int box_y,
                        int box_z) {
+    // rows of nz floats, pitch_z floats apart: columns nz .. pitch_z-1 are outside the tensor (zero filled on load)
     const cuuint64_t gdim[3]    = {(cuuint64_t)nz, (cuuint64_t)ny, (cuuint64_t)nx};
-    const cuuint64_t gstride[2] = {(cuuint64_t)nz * 4, (cuuint64_t)nz * ny * 4};
+    const cuuint64_t gstride[2] = {(cuuint64_t)pitch_z * 4, (cuuint64_t)pitch_z * ny * 4};
     const cuuint32_t box[3]     = {(cuuint32_t)box_z, (cuuint32_t)box_y, (cuuint32_t)box_x};
     const CUresult r = encode_tiled(map, const_cast<float*>(base), gdim, gstride, box);
     if (r != CUDA_SUCCESS) {
@@ -146,7 +147,7 @@ static int get_state_map(pdx_fd_plan* p, const float* ptr, const CUtensorMap** o
         CUtensorMap m;
         int by, bz;
         fd_tma_state_box(&by, &bz);
-        if (make_tensor_map_3d(&m, ptr, p->d.nx, p->d.ny, p->d.nz, 1, by, bz)) return 1;
+        if (make_tensor_map_3d(&m, ptr, p->d.nx, p->d.ny, p->d.nz, p->base.pz, 1, by, bz)) return 1;
         if (p->smaps.size() > 64) p->smaps.clear();
         it = p->smaps.emplace(ptr, m).first;
     }
@@ -158,7 +159,7 @@ static int get_map(pdx_fd_plan* p, const float* ptr, const CUtensorMap** out) {
     auto it = p->maps.find(ptr);
     if (it == p->maps.end()) {
         CUtensorMap m;
-        if (make_tensor_map_3d(&m, ptr, p->d.nx, p->d.ny, p->d.nz, 1, p->box_y, p->box_z)) return 1;
+        if (make_tensor_map_3d(&m, ptr, p->d.nx, p->d.ny, p->d.nz, p->base.pz, 1, p->box_y, p->box_z)) return 1;
         if (p->maps.size() > 64) p->maps.clear();
         it = p->maps.emplace(ptr, m).first;
     }
@@ -255,6 +256,7 @@ void pdx_fd_desc_init(pdx_fd_desc* d) {
 static int fill_args(const pdx_fd_desc& d, FdArgs* a) {
     std::memset(a, 0, sizeof(*a));
     a->nx = d.nx; a->ny = d.ny; a->nz = d.nz;
+    a->pz = d.pitch_z > 0 ? d.pitch_z : d.nz;
     a->has_x = d.ndim == 3;
     a->xb = d.x_begin; a->xe = d.x_end;
     if (a->has_x) {
@@ -290,6 +292,14 @@ int pdx_fd_plan_create(const pdx_fd_desc* din, pdx_fd_plan** out) {
         return 1;
     }
     if (pdx_model_num_states(d.model) < 0) { set_error("pdx_fd_plan_create: unknown model"); return 1; }
+    if (d.pitch_z != 0 && d.pitch_z != d.nz) {
+        if (d.pitch_z < d.nz) { set_error("pdx_fd_plan_create: pitch_z < nz"); return 1; }
+        if (is_lut_model(d.model) || d.lap_kind == PDX_LAP_ANISO || d.kernel == PDX_KERNEL_RESIDENT) {
+            set_error("pdx_fd_plan_create: pitched rows are for the closed-form models with the homogeneous / conv / "
+                      "heterogeneous operators on the per-step kernels");
+            return 1;
+        }
+    }
     if (d.lap_kind < PDX_LAP_HOMOG || d.lap_kind > PDX_LAP_ANISO) { set_error("pdx_fd_plan_create: unknown lap_kind"); return 1; }
     if ((d.lap_kind == PDX_LAP_CONV || d.lap_kind == PDX_LAP_ANISO) && d.ndim == 2) {
         set_error("pdx_fd_plan_create: the conv and anisotropic operators are 3-D only");
@@ -421,7 +431,7 @@ int pdx_fd_plan_prepare_aniso(pdx_fd_plan* p, const float* DIFF, const float* AV
     if (!p->aniso_C) {
         if (check_cuda(cudaMalloc(&p->aniso_C, sizeof(float) * 6 * (size_t)n), "cudaMalloc(anisotropic tensor)")) return 1;
         for (int c = 0; c < 6; ++c)
-            if (make_tensor_map_3d(&p->aniso_maps[c], p->aniso_C + (size_t)c * n, d.nx, d.ny, d.nz, 1, p->box_y, p->box_z)) return 1;
+            if (make_tensor_map_3d(&p->aniso_maps[c], p->aniso_C + (size_t)c * n, d.nx, d.ny, d.nz, d.nz, 1, p->box_y, p->box_z)) return 1;
     }
     if (launch_aniso_tensor(DIFF, AVEC, p->aniso_C, n, (cudaStream_t)stream)) return 1;
     p->aniso_diff = DIFF;

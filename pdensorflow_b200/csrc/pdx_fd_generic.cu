@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) fd_generic_kernel(const __grid_constant__
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int i = a.xb + blockIdx.z;
     if (k >= a.nz || j >= a.ny || i >= a.xe) return;
-    const size_t idx = ((size_t)i * a.ny + j) * a.nz + k;
+    const size_t idx = ((size_t)i * a.ny + j) * a.pz + k;
 
     const Field f = make_field(a);
     float c;
@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(256) fd_generic_kernel(const __grid_constant__
     }
     const float u_new = madd<MATH>(u1, mmul<MATH>(a.coef, lap));
     a.Uout[idx] = u_new;
-    if (a.mirror_lo && i == a.mirror_lo_plane) a.mirror_lo[(size_t)j * a.nz + k] = u_new;
-    if (a.mirror_hi && i == a.mirror_hi_plane) a.mirror_hi[(size_t)j * a.nz + k] = u_new;
+    if (a.mirror_lo && i == a.mirror_lo_plane) a.mirror_lo[(size_t)j * a.pz + k] = u_new;
+    if (a.mirror_hi && i == a.mirror_hi_plane) a.mirror_hi[(size_t)j * a.pz + k] = u_new;
 }
 
 template <int MODEL, int LAP, int MATH, int MODE>
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) enforce_boundary_kernel(const __grid_cons
     const int i = blockIdx.z;
     if (k >= a.nz || j >= a.ny) return;
     const Field f = make_field(a);
-    a.Uout[((size_t)i * a.ny + j) * a.nz + k] = f.at(i, j, k);
+    a.Uout[((size_t)i * a.ny + j) * a.pz + k] = f.at(i, j, k);
 }
 
 int launch_enforce_boundary(const FdArgs& a, cudaStream_t s) {

@@ -349,6 +349,7 @@ const void* pick_kernel(int model, int math, bool two) {
 // the configuration is not covered (heterogeneous operator, Dirichlet pad, lookup-table models).
 bool fd_resident_plan(const pdx_fd_desc& d, ResidentGeom* g) {
     if (d.ndim != 2 || d.lap_kind != PDX_LAP_HOMOG || d.dirichlet) return false;
+    if (d.pitch_z != 0 && d.pitch_z != d.nz) return false;          // contiguous rows only
     if (d.model != PDX_MODEL_NONE && d.model != PDX_MODEL_FENTON4V && d.model != PDX_MODEL_MMS2V && d.model != PDX_MODEL_MS2V)
         return false;
     if (d.nz > 1024 || d.nz < 3 || d.ny < 3) return false;

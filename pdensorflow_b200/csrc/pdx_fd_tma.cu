@@ -150,6 +150,20 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
     const bool lo2 = z < a.zclo, lo1 = z - 1 < a.zclo;
     const bool hi2 = z + 3 > a.zchi, hi1 = z + 4 > a.zchi;
     const bool dlo1 = z - 1 < 0, dhi1 = z + 4 > a.nz - 1;                    // DIFF: symmetric pad only
+    // Pitched rows (nz % 4 != 0, rows padded to a multiple of four: pdx_fd_desc.pitch_z): the clamp column may sit
+    // anywhere among a lane's four columns.  General patch: columns beyond index h take the value at h (h < 0: the
+    // column left of the four, read from shared memory).  zgen is CTA uniform.
+    const bool zgen = (a.nz & 3) != 0;
+    const int hiz = a.zchi - z, hizd = a.nz - 1 - z;
+    auto fixhi = [&](F4& v, const float* rowp, int h) {
+        if (h < 3) {
+            const float tv = h < 0 ? rowp[-1] : (h == 0 ? v.v[0] : (h == 1 ? v.v[1] : v.v[2]));
+            if (h < 0) v.v[0] = tv;
+            if (h < 1) v.v[1] = tv;
+            if (h < 2) v.v[2] = tv;
+            v.v[3] = tv;
+        }
+    };
 
     // row geometry of a y-tile: constant along the march in 3-D, recomputed per marched tile in 2-D
     int  gy[R], rc[R], rm[R], rp[R], drm[R], drp[R], drc0;
@@ -177,7 +191,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (!act[r]) continue;
-            const size_t gi = ((size_t)p * a.ny + gy[r]) * a.nz + z;
+            const size_t gi = ((size_t)p * a.ny + gy[r]) * a.pz + z;
 #pragma unroll
             for (int s = 0; s < NS; ++s) stn[r][s] = ldg4(a.st[s] + gi);
         }
@@ -224,7 +238,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (!act[r]) continue;
-            const size_t gi = ((size_t)p * a.ny + gy[r]) * a.nz + z;
+            const size_t gi = ((size_t)p * a.ny + gy[r]) * a.pz + z;
             F4 c = lds4(Sc + rc[r]);
             float zl = Sc[rc[r] - 1], zr = Sc[rc[r] + 4];
             F4 ym = lds4(Sc + rm[r]), yp = lds4(Sc + rp[r]);
@@ -260,10 +274,19 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
                     zl = (yin && z - 1 >= a.zclo && z - 1 <= a.zchi) ? zl : dv;
                     zr = (yin && z + 4 >= a.zclo && z + 4 <= a.zchi) ? zr : dv;
                 } else if (zb_tile) {
-                    zfix(c, lo2, hi2); zfix(ym, lo2, hi2); zfix(yp, lo2, hi2);
-                    if (HAS_X) { zfix(xm, lo2, hi2); zfix(xp, lo2, hi2); }
-                    zl = lo1 ? c.v[0] : zl;          // after zfix c.v[0] already holds the clamped value
-                    zr = hi1 ? c.v[3] : zr;
+                    if (zgen) {
+                        zfix(c, lo2, false); zfix(ym, lo2, false); zfix(yp, lo2, false);
+                        if (HAS_X) { zfix(xm, lo2, false); zfix(xp, lo2, false); }
+                        zl = lo1 ? c.v[0] : zl;
+                        fixhi(c, Sc + rc[r], hiz); fixhi(ym, Sc + rm[r], hiz); fixhi(yp, Sc + rp[r], hiz);
+                        if (HAS_X) { fixhi(xm, Sm + rc[r], hiz); fixhi(xp, Sp + rc[r], hiz); }
+                        zr = hi1 ? c.v[3] : zr;          // after fixhi c.v[3] holds the clamp column's value
+                    } else {
+                        zfix(c, lo2, hi2); zfix(ym, lo2, hi2); zfix(yp, lo2, hi2);
+                        if (HAS_X) { zfix(xm, lo2, hi2); zfix(xp, lo2, hi2); }
+                        zl = lo1 ? c.v[0] : zl;          // after zfix c.v[0] already holds the clamped value
+                        zr = hi1 ? c.v[3] : zr;
+                    }
                 }
             }
             F4 dc, dym, dyp, dxm, dxp;
@@ -273,6 +296,7 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
                 const int drc = drc0 + min(gy[r], a.ny - 1) * COLS;
                 dc = lds4(Dc + drc);
                 dzl = dlo1 ? dc.v[0] : Dc[drc - 1];
+                if (zgen) fixhi(dc, Dc + drc, hizd);
                 dzr = dhi1 ? dc.v[3] : Dc[drc + 4];
                 dym = lds4(Dc + drm[r]); dyp = lds4(Dc + drp[r]);
                 if (HAS_X) { dxm = lds4(slotD(jc - qs) + drc); dxp = lds4(slotD(jc + qs) + drc); }
@@ -312,8 +336,8 @@ fd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ 
             }
             stg4(a.Uout + gi, out);
             if (HAS_X) {   // fused halo store into the neighbours' ghost planes (peer memory over NVLink)
-                if (a.mirror_lo && p == a.mirror_lo_plane) stg4(a.mirror_lo + (size_t)gy[r] * a.nz + z, out);
-                if (a.mirror_hi && p == a.mirror_hi_plane) stg4(a.mirror_hi + (size_t)gy[r] * a.nz + z, out);
+                if (a.mirror_lo && p == a.mirror_lo_plane) stg4(a.mirror_lo + (size_t)gy[r] * a.pz + z, out);
+                if (a.mirror_hi && p == a.mirror_hi_plane) stg4(a.mirror_hi + (size_t)gy[r] * a.pz + z, out);
             }
 #pragma unroll
             for (int s = 0; s < NS; ++s) stg4(a.st[s] + gi, stc[r][s]);
@@ -389,7 +413,8 @@ int launch_het(bool het, int math, bool tst, const FdArgs& a, const CUtensorMap&
 }  // namespace
 
 bool fd_tma_supported(const pdx_fd_desc& d) {
-    if (d.nz % 4 != 0 || d.nz < 4) return false;
+    const int pz = d.pitch_z > 0 ? d.pitch_z : d.nz;
+    if (pz % 4 != 0 || d.nz < 3) return false;          // tensor maps need rows that are 16-byte multiples
     if (d.lap_kind == PDX_LAP_CONV && d.math_mode == PDX_MATH_EXACT) return false;   // different rounding order
     if (d.ny < 3) return false;
     return true;

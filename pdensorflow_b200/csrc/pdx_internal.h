@@ -25,6 +25,7 @@ struct FdArgs {
     float* mirror_hi;
     int mirror_lo_plane, mirror_hi_plane;
     int nx, ny, nz;
+    int pz;                      // floats between consecutive rows (= nz unless the arrays are pitched)
     int xb, xe;                  // planes advanced
     int xclo, xchi;              // clamp of stencil plane indices for U (enforce_boundary + pad)
     int yclo, ychi, zclo, zchi;  // same for the y / z axes
@@ -90,7 +91,7 @@ bool fd_tma_supported(const pdx_fd_desc& d);
 int  launch_fd_tma(const pdx_fd_desc& d, const FdArgs& a, const CUtensorMap& mapU, const CUtensorMap& mapD,
                    const CUtensorMap* const* mapS, cudaStream_t s);
 void fd_tma_state_box(int* box_y, int* box_z);
-int  make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int nz, int box_x, int box_y,
+int  make_tensor_map_3d(CUtensorMap* map, const float* base, int nx, int ny, int nz, int pitch_z, int box_x, int box_y,
                         int box_z);
 // geometry of the TMA kernel's tile, needed by the host to build the tensor maps
 void fd_tma_tile_geometry(const pdx_fd_desc& d, int* tile_y, int* tile_z, int* box_y, int* box_z);

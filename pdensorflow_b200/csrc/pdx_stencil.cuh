@@ -19,7 +19,7 @@ __device__ __forceinline__ int clampi_(int v, int lo, int hi) { return min(max(v
 
 struct Field {
     const float* U;
-    int ny, nz;
+    int ny, nz, pz;
     int xclo, xchi, yclo, ychi, zclo, zchi;
     int dirichlet;
     float dval;
@@ -27,17 +27,17 @@ struct Field {
     __device__ __forceinline__ float at(int i, int j, int k) const {
         if (dirichlet) {
             const bool inside = i >= xclo && i <= xchi && j >= yclo && j <= ychi && k >= zclo && k <= zchi;
-            return inside ? U[((size_t)i * ny + j) * nz + k] : dval;
+            return inside ? U[((size_t)i * ny + j) * pz + k] : dval;
         }
         i = clampi_(i, xclo, xchi);
         j = clampi_(j, yclo, ychi);
         k = clampi_(k, zclo, zchi);
-        return U[((size_t)i * ny + j) * nz + k];
+        return U[((size_t)i * ny + j) * pz + k];
     }
 };
 
 __device__ __forceinline__ Field make_field(const FdArgs& a) {
-    return Field{a.Uin, a.ny, a.nz, a.xclo, a.xchi, a.yclo, a.ychi, a.zclo, a.zchi, a.dirichlet, a.dirichlet_value};
+    return Field{a.Uin, a.ny, a.nz, a.pz, a.xclo, a.xchi, a.yclo, a.ychi, a.zclo, a.zchi, a.dirichlet, a.dirichlet_value};
 }
 
 // 19-point fibre-tensor operator.  DIFF is [nx][ny][nz][2] = (sigma_t, sigma_l - sigma_t),
@@ -111,7 +111,7 @@ __device__ __forceinline__ float node_laplacian(const FdArgs& a, const Field& f,
         lap = xadd(xadd(gx, gy), gz);
     } else if (LAP == PDX_LAP_HETEROG) {
         const float* D = a.DIFF;
-        auto dat = [&](int ii, int jj, int kk) { return D[((size_t)ii * a.ny + jj) * a.nz + kk]; };
+        auto dat = [&](int ii, int jj, int kk) { return D[((size_t)ii * a.ny + jj) * a.pz + kk]; };
         const float dc = dat(i, j, k);
         lap = lap_axis_het<MATH>(f.at(i, jm, k), c, f.at(i, jp, k), dat(i, jm, k), dc, dat(i, jp, k), a.hysq, a.rhysq);
         if (a.has_x) {

@@ -167,6 +167,15 @@ class FDStepper:
             d.nx, d.ny, d.nz = 1, shape[0], shape[1]
             d.dy, d.dz = (float(np.float32(s)) for s in spacing)
         self.array_shape = (d.nx, d.ny, d.nz) if self.ndim == 3 else (d.ny, d.nz)
+        # Rows that are not 16-byte multiples (nz % 4 != 0) cannot be tiled by tensor maps: the stepper then keeps ITS
+        # arrays (U pair, gates, DIFF) with rows padded to a multiple of four floats (pdx_fd_desc.pitch_z) and hands out
+        # [..., :nz] views, so the tile kernel runs at full speed; caller-owned buffers, the lookup-table models and
+        # the anisotropic operator keep contiguous rows (one-thread-per-node kernel).
+        self.pitch = d.nz
+        if (d.nz % 4 != 0 and buffers is None and part is None and not self.is_lut and lap != 'aniso'
+                and kernel not in ('generic', 'resident')):
+            self.pitch = (d.nz + 3) // 4 * 4
+            d.pitch_z = self.pitch
         d.dt = float(np.float32(dt))
         d.coef = float(np.float32(dt)) if lap in ('heterog', 'aniso') else float(np.float32(float(diff) * float(dt)))
         d.lap_kind, d.model = self.lap_id, self.model_id
@@ -195,8 +204,8 @@ class FDStepper:
                 if tuple(b.shape) != tuple(self.array_shape) or b.dtype != torch.float32 or not b.is_contiguous():
                     raise ValueError('buffers must be contiguous fp32 tensors of the array shape')
         else:
-            self.Ua = torch.empty(self.array_shape, dtype=torch.float32, device=self.device)
-            self.Ub = torch.empty_like(self.Ua)
+            self.Ua = self._new_field(0.0)
+            self.Ub = self._new_field(0.0)
         if self.is_lut:
             # the model instance owns tables, constants and the 19/22 state arrays
             self.ionic._dt = dt
@@ -204,13 +213,16 @@ class FDStepper:
             self.states = self.ionic.state_tensors()
             L.check(L.lib().pdx_fd_plan_set_lut(self._plan, C.byref(self.ionic.lut_desc())))
         else:
-            self.states = [torch.full(self.array_shape, v, dtype=torch.float32, device=self.device)
-                           for v in STATE_INIT[self.model_id]]
+            self.states = [self._new_field(v) for v in STATE_INIT[self.model_id]]
         self.DIFF = self.AVEC = None
         if lap == 'heterog':
             if DIFF is None:
                 raise ValueError("lap='heterog' needs DIFF")
             self.DIFF = self._to_device(DIFF)
+            if self.pitch != self.array_shape[-1]:
+                t = self._new_field(0.0)
+                t.copy_(self.DIFF)
+                self.DIFF = t
         elif lap == 'aniso':
             if DIFF is None or AVEC is None:
                 raise ValueError("lap='aniso' needs DIFF [W,H,D,2] and AVEC [W,H,D,6]")
@@ -245,6 +257,15 @@ class FDStepper:
         with torch.cuda.device(self.device):
             L.check(L.lib().pdx_fd_plan_prepare_aniso(self._plan, L.ptr(self.DIFF), L.ptr(self.AVEC), L.stream_ptr()))
         return True
+
+    def _new_field(self, value):
+        """A field of the stepper's array shape; pitched steppers: a [..., :nz] view of rows padded to ``pitch`` floats
+        (its data_ptr is the padded array's, which is what the library addresses)."""
+        nz = self.array_shape[-1]
+        if self.pitch == nz:
+            return torch.full(self.array_shape, value, dtype=torch.float32, device=self.device)
+        full = torch.full(tuple(self.array_shape[:-1]) + (self.pitch,), value, dtype=torch.float32, device=self.device)
+        return full[..., :nz]
 
     def _to_device(self, A, extra=()):
         if isinstance(A, torch.Tensor):
@@ -340,6 +361,12 @@ class FDStepper:
         ``mask`` is a contiguous fp32 CUDA tensor of the stepper's array shape (ghost planes included for slabs)."""
         U = self.current_U()
         self._check_field(mask, 'stimulus mask')
+        if self.pitch != self.array_shape[-1]:
+            # pitched rows: the flat stimulus kernel does not apply; the same arithmetic as tensor operations (rare call)
+            with torch.cuda.device(self.device), torch.cuda.stream(torch.cuda.current_stream(self.device) if stream is None else stream):
+                v = mask * float(np.float32(intensity))
+                U.copy_(torch.maximum(U, v) if everywhere else torch.where(v != 0, torch.maximum(U, v), U))
+            return
         fn = L.lib().pdx_stim_apply_max if everywhere else L.lib().pdx_stim_apply
         with torch.cuda.device(self.device):
             L.check(fn(L.ptr(U), L.ptr(mask), float(np.float32(intensity)), U.numel(), self._stream(stream)))
@@ -529,6 +556,8 @@ class FrameStreamer:
         if steps % 2:
             raise ValueError('frames use an even number of steps (ping-pong parity)')
         self.fd, self.steps, self.skew, self.advance = stepper, int(steps), bool(skew), advance
+        if getattr(stepper, 'pitch', stepper.array_shape[-1]) != stepper.array_shape[-1]:
+            raise L.PdxError('FrameStreamer moves whole contiguous planes: grids with nz % 4 != 0 (pitched rows) are not streamed')
         dev = stepper.device
         # planes [x0, x1) of the array are the ones that travel (a slab leaves its ghost planes out)
         self.x0, self.x1 = planes if planes is not None else (0, stepper.array_shape[0])

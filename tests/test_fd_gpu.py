@@ -313,6 +313,53 @@ def test_anisotropic_tile_kernel(cuda, shape, chunk, model):
     assert rel_l2(res['fast'][0], Uo) <= TOL['fast']
 
 
+ROW_SHAPES = [(9, 11, 13), (12, 20, 133), (7, 9, 262), (5, 6, 5), (4, 3, 3), (19, 131), (40, 13), (9, 258)]
+
+
+@pytest.mark.parametrize('shape', ROW_SHAPES)
+@pytest.mark.parametrize('lap', ['homog', 'heterog'])
+@pytest.mark.parametrize('model', [None, 'fenton4v', 'mms2v'])
+def test_rows_that_are_not_16_byte_multiples_on_the_tile_kernel(cuda, shape, lap, model):
+    """nz % 4 != 0: the stepper keeps its arrays with rows padded to a multiple of four floats (pdx_fd_desc.pitch_z) and the
+    tile kernel runs on them - bitwise the one-thread-per-node kernel on contiguous rows in EXACT arithmetic, x chunks,
+    the Dirichlet pad and a stimulus included; FAST within 1e-5 of the oracle."""
+    from pdensorflow_b200.fd import FDStepper
+    rng = np.random.default_rng(53)
+    U, states = random_fields(shape, seed=59)
+    states = states[:NSTATES[model]]
+    DIFF = (0.2 + rng.random(shape)).astype(np.float32) if lap == 'heterog' else None
+    spacing = (1.0, 0.9, 1.1)[:len(shape)]
+    for dirichlet in (None, 2.5):
+        res = {}
+        for tag, kernel, math, chunk in (('tile', 'tma', 'exact', 0), ('chunk3', 'tma', 'exact', 3), ('generic', 'generic', 'exact', 0),
+                                         ('fast', 'auto', 'fast', 0)):
+            st = FDStepper(shape, spacing, 0.05, 0.8, model=model, lap=lap, DIFF=DIFF, math=math, kernel=kernel,
+                           dirichlet=dirichlet, x_chunk=chunk)
+            assert st.kernel == ('generic' if kernel == 'generic' else 'tma')
+            assert (st.pitch != shape[-1]) == (kernel != 'generic') and st.U().shape == tuple(shape)
+            st.set_U(U)
+            if states:
+                st.set_states(states)
+            st.step(2)
+            mask = torch.zeros(shape, device='cuda')
+            mask[..., : shape[-1] // 2] = 1.0
+            st.apply_stimulus(mask, 30.0)
+            st.step(1)
+            res[tag] = [st.U().cpu().numpy()] + [x.cpu().numpy() for x in st.states]
+        for tag in ('tile', 'chunk3'):
+            for a, b in zip(res[tag], res['generic']):
+                assert np.array_equal(a, b), (tag, dirichlet)
+        m = make_oracle(model, 0.05, states)
+        Uo = U.copy()
+        for k in range(3):
+            Uo = ofd.fd_step(m, Uo, 0.05, 0.8, spacing, DIFF=DIFF, dirichlet=dirichlet)
+            if k == 1:
+                mk = np.zeros(shape, np.float32)
+                mk[..., : shape[-1] // 2] = 1.0
+                Uo = np.where(mk != 0, np.maximum(Uo, np.float32(30.0) * mk), Uo).astype(np.float32)
+        assert rel_l2(res['fast'][0].reshape(shape), Uo) <= TOL['fast']
+
+
 def test_x_chunking_is_invisible(cuda):
     """The TMA kernel marches x in chunks with 2 halo planes: results must not depend on the chunk."""
     from pdensorflow_b200.fd import FDStepper

@@ -87,6 +87,15 @@ if __name__ == '__main__':
         bench(A, lap='aniso', nsteps=4, kernel='generic')
         bench(A, lap='aniso', nsteps=4, kernel='generic', math='exact')
         sys.exit(0)
+    if '--odd' in sys.argv:            # nz % 4 != 0: row-wise TMA variant of the tile kernel vs the one-thread-per-node kernel
+        O = (512, 512, 510)
+        bench(O, kernel='tma')
+        bench(O, kernel='generic')
+        bench(O, kernel='tma', lap='heterog')
+        bench(O, kernel='tma', model='mms2v')
+        bench((4096, 4090), nsteps=100, kernel='tma')
+        bench(S)                        # the bench kernel itself, same run
+        sys.exit(0)
     if '--2d' in sys.argv:             # 2-D grids on the per-step TMA kernel (y-march) and the generic kernel
         for n2 in (4096, 2048, 1024):
             bench((n2, n2), nsteps=200, kernel='tma')
