@@ -361,6 +361,9 @@ int     pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_worksp
                             int32_t max_window, pdx_pcg_part** out);
 void    pdx_pcg_part_destroy(pdx_pcg_part* s);
 int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s);
+int32_t pdx_pcg_part_threads(const pdx_pcg_part* s);        /* threads per block of the cooperative grid */
+int32_t pdx_pcg_part_stage_bytes(const pdx_pcg_part* s);    /* > 0: q = A p streams the SELL slices through a shared-memory
+                                                               ring of this slot size (copy engine), 0: per-thread loads */
 /* Diagnostics: when device_stamps != NULL, thread 0 of every following solve writes %globaltimer (ns) at each phase
  * boundary: [0] end of the set-up product, [1] after its all-reduce, then per iteration: end of q = A p, after the
  * all-reduce, end of the x / r update, after the all-reduce, end of the p update, after the closing grid barrier. */

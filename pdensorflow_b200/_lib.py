@@ -114,6 +114,8 @@ _SIGNATURES = {
     'pdx_pcg_part_create': (C.c_int, [C.POINTER(PcgPartDesc), C.POINTER(_P), C.c_int32, C.POINTER(_P)]),
     'pdx_pcg_part_destroy': (None, [_P]),
     'pdx_pcg_part_blocks': (C.c_int32, [_P]),
+    'pdx_pcg_part_threads': (C.c_int32, [_P]),
+    'pdx_pcg_part_stage_bytes': (C.c_int32, [_P]),
     'pdx_pcg_part_set_profile': (C.c_int, [_P, _P, C.c_int32]),
     'pdx_pcg_part_solve': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P]),
 }

@@ -21,8 +21,11 @@
 //    involvement, no extra launch.  A rank that never shows up makes block 0 time out (timeout_ms) and
 //    the solve return flag bit 2 instead of hanging the GPU.
 #include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
+#include <vector>
 #include "pdx_internal.h"
 #include "pdx_fem_dev.cuh"
 
@@ -130,6 +133,7 @@ struct PartArgs {
     int32_t* info;
     unsigned long long* prof;        // optional: block 0 stamps %globaltimer at every phase boundary (diagnostics)
     int nprof;
+    int stage_slot_bytes;            // > 0: SELL slices of q = A p are staged through shared memory by the copy engine
     int keep;                        // L2 policy bits: 1 p, 2 r, 4 q, 8 x, 16 minv evict-last; 32 matrix evict-first
 };
 
@@ -275,8 +279,90 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, const Pol& pol, l2po
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant__ PartArgs a) {
+// ---- SELL product with the matrix stream on the copy engine (r02).  In rows_dot a warp reads slice_ptr, then the
+// slice's col / val words, then gathers: three dependent latencies per slice, and only the middle one moves the 480 MB
+// that bound the phase (ncu: 0.25 eligible warps per scheduler).  Here lane 0 of every warp keeps STAGE_NB slices
+// ahead in flight as cp.async.bulk copies (col and val words of a slice are contiguous: two copies, one mbarrier)
+// into a per-warp shared-memory ring; the lanes then read their columns from shared memory and have a whole row of
+// gathers in flight at once.  Products are accumulated in the same order as in rows_dot: same bits.
+constexpr int STAGE_NB = 2;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct StageState {
+    unsigned int uses;       // slots consumed so far by this warp (phase parity of the ring's mbarriers)
+};
+
+template <class F>
+__device__ __forceinline__ void rows_dot_staged(const PartArgs& a, const Pol& pol, l2pol_t polx, const float* vals,
+                                                const float* xa, StageState& stg, F&& f) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    const int slot = a.stage_slot_bytes;
+    unsigned char* ring = dsm + (size_t)wib * STAGE_NB * slot;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + (size_t)nwb * STAGE_NB * slot) + wib * STAGE_NB;
+    int* widths = reinterpret_cast<int*>(dsm + (size_t)nwb * STAGE_NB * (slot + 8)) + wib * STAGE_NB;
+    const int gw = blockIdx.x * nwb + wib, nw = gridDim.x * nwb;
+    const int nsl = (a.n + 31) >> 5;
+    const int cnt = gw < nsl ? (nsl - gw + nw - 1) / nw : 0;          // slices gw, gw + nw, ... of this warp
+
+    auto issue = [&](int t, int beg, int end) {          // lane 0
+        const int sl = (int)((stg.uses + t) % STAGE_NB);
+        const uint32_t bytes = (uint32_t)(end - beg) * 4u;
+        const uint32_t bar = smem_addr(&bars[sl]);
+        widths[sl] = (end - beg) >> 5;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+        const uint32_t dst = smem_addr(ring + (size_t)sl * slot);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(dst), "l"(a.col + beg), "r"(bytes), "r"(bar), "l"(pol.mat) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(dst + bytes), "l"(vals + beg), "r"(bytes), "r"(bar), "l"(pol.mat) : "memory");
+    };
+    if (lane == 0) {
+        for (int t = 0; t < STAGE_NB && t < cnt; ++t) {
+            const int s0 = gw + t * nw;
+            issue(t, a.rowptr[s0], a.rowptr[s0 + 1]);
+        }
+    }
+    for (int t = 0; t < cnt; ++t) {
+        int nbeg = 0, nend = 0;
+        const bool refill = lane == 0 && t + STAGE_NB < cnt;
+        if (refill) {                                    // slice_ptr of the refill: loaded now, used after the products
+            const int s1 = gw + (t + STAGE_NB) * nw;
+            nbeg = a.rowptr[s1]; nend = a.rowptr[s1 + 1];
+        }
+        const unsigned int use = stg.uses + t;
+        const int sl = (int)(use % STAGE_NB);
+        const uint32_t bar = smem_addr(&bars[sl]), parity = (use / STAGE_NB) & 1u;
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        const int w = widths[sl];
+        const int32_t* scol = reinterpret_cast<const int32_t*>(ring + (size_t)sl * slot) + lane;
+        const float* sval = reinterpret_cast<const float*>(ring + (size_t)sl * slot + (size_t)w * 128) + lane;
+        float acc = 0.0f;
+        int k = 0;
+        for (; k + 4 <= w; k += 4) {
+            const int c0 = scol[k * 32], c1 = scol[k * 32 + 32], c2 = scol[k * 32 + 64], c3 = scol[k * 32 + 96];
+            const float x0 = ldv(xa + c0, polx), x1 = ldv(xa + c1, polx), x2 = ldv(xa + c2, polx), x3 = ldv(xa + c3, polx);
+            acc = fmaf(sval[k * 32], x0, acc);
+            acc = fmaf(sval[k * 32 + 32], x1, acc);
+            acc = fmaf(sval[k * 32 + 64], x2, acc);
+            acc = fmaf(sval[k * 32 + 96], x3, acc);
+        }
+        for (; k < w; ++k) acc = fmaf(sval[k * 32], ldv(xa + scol[k * 32], polx), acc);
+        const int row = (gw + t * nw) * 32 + lane;
+        if (row < a.n) f(row, acc, 0.0f);
+        __syncwarp();                                    // every lane is done with the slot
+        if (refill) issue(t + STAGE_NB, nbeg, nend);
+    }
+    stg.uses += (unsigned int)cnt;
+}
+
+// STAGED (G == 0 only): blocks of at most 512 threads with the shared-memory ring, 64 registers per thread
+template <int G, bool STAGED = false>
+__global__ void __launch_bounds__(STAGED ? 512 : 1024, 2) pcg_part_kernel(const __grid_constant__ PartArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float sh[33];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,6 +370,19 @@ __global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant
     const int glo = a.glo;
     const int hi_first = a.n - a.send_hi;          // first row the upper neighbour holds as a ghost
     unsigned int epoch = *((volatile unsigned int*)&a.comm->epoch);
+    constexpr int UNR = STAGED ? 4 : 1;      // rows per thread and trip of the vector passes (32-register kernels: 1)
+    StageState stg{0u};
+    if constexpr (STAGED) {
+        extern __shared__ __align__(128) unsigned char dsm[];
+        const int nwb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+        uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + (size_t)nwb * STAGE_NB * a.stage_slot_bytes) + wib * STAGE_NB;
+        if ((threadIdx.x & 31) == 0) {
+            for (int i = 0; i < STAGE_NB; ++i)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[i])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     Pol pol;
     pol.mat  = l2_policy(a.keep & 32 ? 2 : 0);
     pol.p    = l2_policy(a.keep & 1 ? 1 : 0);
@@ -295,7 +394,7 @@ __global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant
     // b = M rhs0 (optional) ; r = b - A x ; z = Minv r ; p = z ; rz = r.z      (conjgrad.py:191-203)
     float loc_rz = 0.0f, loc_rr = 0.0f;
     bool pushed = false;
-    rows_dot<G>(a, pol, pol.x, a.x, a.mval, a.rhs0, [&](int row, float ax, float bm) {
+    auto take_r = [&](int row, float ax, float bm) {
         const float bv = a.mval ? bm : a.b[row];
         const float r = __fsub_rn(bv, ax);
         const float z = a.minv ? __fmul_rn(ldv(a.minv + row, pol.minv), r) : r;
@@ -305,7 +404,16 @@ __global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant
         if (row >= hi_first) { a.peer_hi_p[row - hi_first] = z; pushed = true; }
         loc_rz = fmaf(r, z, loc_rz);
         loc_rr = fmaf(r, r, loc_rr);
-    });
+    };
+    if constexpr (STAGED) {
+        // two staged products (b = M rhs0 parked in q, then A x) instead of one pass over three arrays: the ring slot
+        // stays two arrays wide; a row is handled by the same lane in both, so no synchronisation in between
+        if (a.mval)
+            rows_dot_staged(a, pol, pol.x, a.mval, a.rhs0, stg, [&](int row, float bm, float) { a.q[row] = bm; });
+        rows_dot_staged(a, pol, pol.x, a.aval, a.x, stg, [&](int row, float ax, float) { take_r(row, ax, a.mval ? a.q[row] : 0.0f); });
+    } else {
+        rows_dot<G>(a, pol, pol.x, a.x, a.mval, a.rhs0, take_r);
+    }
     int nstamp = 0;
     auto stamp = [&]() {
         if (a.prof && tid == 0 && nstamp < a.nprof) a.prof[nstamp] = global_ns();
@@ -321,10 +429,12 @@ __global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant
         niters = k;
         // q = A p ; pq = p.q
         float loc_pq = 0.0f;
-        rows_dot<G>(a, pol, pol.p, a.p, nullptr, nullptr, [&](int row, float ap, float) {
+        auto take_q = [&](int row, float ap, float) {
             stv(a.q + row, ap, pol.q);
             loc_pq = fmaf(ldv(a.p + glo + row, pol.p), ap, loc_pq);
-        });
+        };
+        if constexpr (STAGED) rows_dot_staged(a, pol, pol.p, a.aval, a.p, stg, take_q);
+        else rows_dot<G>(a, pol, pol.p, a.p, nullptr, nullptr, take_q);
         float pq, unused;
         stamp();
         ok = all_reduce<1>(a, grid, epoch, sh, loc_pq, 0.0f, &pq, &unused, false);
@@ -334,20 +444,37 @@ __global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant
         // x += alpha p ; r -= alpha q ; res = r.r ; z = Minv r ; rz' = r.z        (conjgrad.py:172-183)
         loc_rz = 0.0f; loc_rr = 0.0f;
         pushed = false;
-        for (int i = tid; i < a.n; i += nthreads) {
-            const float pi = ldv(a.p + glo + i, pol.p);
-            const float xi = ldv(a.x + glo + i, pol.x);
-            const float qi = ldv(a.q + i, pol.q);
-            const float ri = ldv(a.r + i, pol.r);
-            const float mi = a.minv ? ldv(a.minv + i, pol.minv) : 1.0f;
-            stv(a.x + glo + i, fmaf(alpha, pi, xi), pol.x);
-            const float r = fmaf(-alpha, qi, ri);
-            stv(a.r + i, r, pol.r);
-            const float z = a.minv ? __fmul_rn(mi, r) : r;
-            if (i < a.send_lo) { a.peer_lo_zg[i] = z; pushed = true; }            // edge rows: z into the neighbours' ghost slots
-            if (i >= hi_first) { a.peer_hi_zg[i - hi_first] = z; pushed = true; }
-            loc_rr = fmaf(r, r, loc_rr);
-            loc_rz = fmaf(r, z, loc_rz);
+        // (STAGED: four rows per thread and trip, all twenty loads first - the pass is latency bound otherwise, the staged form
+        //  runs it with a third of the threads; rows are taken in the same order as a plain grid-stride loop)
+        {
+            auto row_update = [&](int i, float pi, float xi, float qi, float ri, float mi) {
+                stv(a.x + glo + i, fmaf(alpha, pi, xi), pol.x);
+                const float r = fmaf(-alpha, qi, ri);
+                stv(a.r + i, r, pol.r);
+                const float z = a.minv ? __fmul_rn(mi, r) : r;
+                if (i < a.send_lo) { a.peer_lo_zg[i] = z; pushed = true; }            // edge rows: z into the neighbours' ghost slots
+                if (i >= hi_first) { a.peer_hi_zg[i - hi_first] = z; pushed = true; }
+                loc_rr = fmaf(r, r, loc_rr);
+                loc_rz = fmaf(r, z, loc_rz);
+            };
+            int i = tid;
+            for (; UNR > 1 && i + (UNR - 1) * nthreads < a.n; i += UNR * nthreads) {
+                float pi[UNR], xi[UNR], qi[UNR], ri[UNR], mi[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = i + u * nthreads;
+                    pi[u] = ldv(a.p + glo + j, pol.p);
+                    xi[u] = ldv(a.x + glo + j, pol.x);
+                    qi[u] = ldv(a.q + j, pol.q);
+                    ri[u] = ldv(a.r + j, pol.r);
+                    mi[u] = a.minv ? ldv(a.minv + j, pol.minv) : 1.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) row_update(i + u * nthreads, pi[u], xi[u], qi[u], ri[u], mi[u]);
+            }
+            for (; i < a.n; i += nthreads)
+                row_update(i, ldv(a.p + glo + i, pol.p), ldv(a.x + glo + i, pol.x), ldv(a.q + i, pol.q), ldv(a.r + i, pol.r),
+                           a.minv ? ldv(a.minv + i, pol.minv) : 1.0f);
         }
         // ghost x, recomputed exactly as its owner computes it
         for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
@@ -370,11 +497,29 @@ __global__ void __launch_bounds__(1024, 2) pcg_part_kernel(const __grid_constant
         if (k == a.maxiter) break;
         const float beta = rznew / rz;
         // p = z + beta p, owned rows and ghosts alike
-        for (int i = tid; i < a.n; i += nthreads) {
-            const float r = ldv(a.r + i, pol.r);
-            const float pi = ldv(a.p + glo + i, pol.p);
-            const float z = a.minv ? __fmul_rn(ldv(a.minv + i, pol.minv), r) : r;
-            stv(a.p + glo + i, fmaf(beta, pi, z), pol.p);
+        {
+            int i = tid;
+            for (; UNR > 1 && i + (UNR - 1) * nthreads < a.n; i += UNR * nthreads) {
+                float ri[UNR], pi[UNR], mi[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = i + u * nthreads;
+                    ri[u] = ldv(a.r + j, pol.r);
+                    pi[u] = ldv(a.p + glo + j, pol.p);
+                    mi[u] = a.minv ? ldv(a.minv + j, pol.minv) : 1.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const float z = a.minv ? __fmul_rn(mi[u], ri[u]) : ri[u];
+                    stv(a.p + glo + i + u * nthreads, fmaf(beta, pi[u], z), pol.p);
+                }
+            }
+            for (; i < a.n; i += nthreads) {
+                const float r = ldv(a.r + i, pol.r);
+                const float pi = ldv(a.p + glo + i, pol.p);
+                const float z = a.minv ? __fmul_rn(ldv(a.minv + i, pol.minv), r) : r;
+                stv(a.p + glo + i, fmaf(beta, pi, z), pol.p);
+            }
         }
         for (int g = tid; g < a.glo + a.ghi; g += nthreads) {
             const int w = g < a.glo ? g : a.n + g;
@@ -412,6 +557,8 @@ struct pdx_pcg_part {
     int window;
     int64_t nnz;
     int G, nblocks, nthreads;
+    int stage_slot_bytes;   // SELL slices staged by the copy engine (0 = off)
+    size_t smem_bytes;
     char* ws;               // own workspace
     float *p, *zg;          // windows inside the workspace (written by the neighbours)
     float* work;            // r, q
@@ -465,12 +612,59 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
     // block adds up; same 32-register budget and occupancy as 8 x 256), small ones 256.  PDX_PCG_PART_THREADS overrides.
     int bt = (long long)d->n_local * (s->G > 0 ? s->G : 1) >= 1000000LL ? 1024 : 256;
     if (const char* e = getenv("PDX_PCG_PART_THREADS")) { const int v = atoi(e); if (v == 256 || v == 512 || v == 1024) bt = v; }
-    s->nthreads = bt;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e;
+    s->stage_slot_bytes = 0;
+    s->smem_bytes = 0;
+    {   // SELL systems large enough to be bandwidth bound: the matrix stream of q = A p goes through the copy engine
+        // (rows_dot_staged).  The ring slot holds the widest slice; the block size is the one that keeps most warps
+        // resident next to STAGE_NB slots per warp.  PDX_PCG_STAGE=0 turns it off (A/B runs).
+        const char* ev = getenv("PDX_PCG_STAGE");
+        // PDX_PCG_STAGE=1 forces it for any SELL system (tests)
+        if (s->G == 0 && (bt == 1024 || (ev && ev[0] == '1')) && !(ev && ev[0] == '0')) {
+            const int nsl = (d->n_local + 31) / 32;
+            std::vector<int32_t> sp((size_t)nsl + 1);
+            if (check_cuda(cudaMemcpy(sp.data(), d->rowptr, sizeof(int32_t) * ((size_t)nsl + 1), cudaMemcpyDeviceToHost), "read slice_ptr")) {
+                delete s; return 1;
+            }
+            int wmax = 0;
+            for (int i = 0; i < nsl; ++i) wmax = std::max(wmax, (sp[i + 1] - sp[i]) / 32);
+            const int slot = wmax * 256;                       // col + val words of the widest slice
+            int smem_max = 0;
+            cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            int best_bt = 0, best_warps = 0;
+            if (getenv("PDX_DEBUG")) fprintf(stderr, "[pdx] stage wmax %d slot %d smem_max %d col %p aval %p\n", wmax, slot, smem_max, (void*)d->col, (void*)d->aval);
+            size_t best_smem = 0;
+            if (slot > 0 && ((uintptr_t)d->col % 16) == 0 && ((uintptr_t)d->aval % 16) == 0) {
+                // the occupancy query counts against the kernel's CURRENT dynamic shared-memory limit: raise it first
+                cudaFuncAttributes fa{};
+                int max_dyn = 0;
+                if (cudaFuncGetAttributes(&fa, pcg_part_kernel<0, true>) == cudaSuccess) max_dyn = smem_max - (int)fa.sharedSizeBytes;
+                if (max_dyn > 0 && cudaFuncSetAttribute(pcg_part_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) == cudaSuccess) {
+                    for (int cand : {512, 384, 256}) {
+                        const size_t need = (size_t)(cand / 32) * STAGE_NB * ((size_t)slot + 8 + 4) + 128;
+                        if (need > (size_t)max_dyn) continue;
+                        int blk = 0;
+                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blk, pcg_part_kernel<0, true>, cand, need) != cudaSuccess) continue;
+                        const int warps = blk * cand / 32;
+                        if (getenv("PDX_DEBUG")) fprintf(stderr, "[pdx] stage cand %d need %zu blk %d wmax %d\n", cand, need, blk, wmax);
+                        if (warps > best_warps) { best_warps = warps; best_bt = cand; best_smem = need; }
+                    }
+                }
+                cudaGetLastError();
+            }
+            if (best_warps >= 16) {
+                bt = best_bt;
+                s->stage_slot_bytes = slot;
+                s->smem_bytes = best_smem;
+            }
+        }
+    }
+    s->nthreads = bt;
     switch (s->G) {
-        case 0:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<0>, bt, 0); break;
+        case 0:  e = s->stage_slot_bytes > 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<0, true>, bt, s->smem_bytes)
+                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<0>, bt, 0); break;
         case 4:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<4>, bt, 0); break;
         case 8:  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<8>, bt, 0); break;
         case 16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_part_kernel<16>, bt, 0); break;
@@ -522,6 +716,7 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
         a.peer_hi_p  = (float*)(w + COMM_BYTES) + d->upper_window_index;
         a.peer_hi_zg = (float*)(w + COMM_BYTES + vec) + d->upper_window_index;
     }
+    a.stage_slot_bytes = s->stage_slot_bytes;
     a.rank = d->rank; a.world = d->world;
     a.timeout_ns = (unsigned long long)(d->timeout_ms > 0 ? d->timeout_ms : 10000) * 1000000ull;
     // L2 residency: vectors that fit ~3/4 of the L2 (in order of re-use: p, r, q, x, Minv) are kept with evict-last,
@@ -548,6 +743,8 @@ void pdx_pcg_part_destroy(pdx_pcg_part* s) {
 }
 
 int32_t pdx_pcg_part_blocks(const pdx_pcg_part* s) { return s ? s->nblocks : 0; }
+int32_t pdx_pcg_part_threads(const pdx_pcg_part* s) { return s ? s->nthreads : 0; }
+int32_t pdx_pcg_part_stage_bytes(const pdx_pcg_part* s) { return s ? s->stage_slot_bytes : 0; }
 
 int pdx_pcg_part_set_profile(pdx_pcg_part* s, uint64_t* device_stamps, int32_t nstamps) {
     if (!s) { set_error("pdx_pcg_part_set_profile: null handle"); return 1; }
@@ -575,14 +772,14 @@ int pdx_pcg_part_solve(pdx_pcg_part* s, const float* b, const float* rhs0, float
     void* args[] = {&a};
     const void* fn;
     switch (s->G) {
-        case 0:  fn = (const void*)pcg_part_kernel<0>; break;
+        case 0:  fn = s->stage_slot_bytes > 0 ? (const void*)pcg_part_kernel<0, true> : (const void*)pcg_part_kernel<0>; break;
         case 4:  fn = (const void*)pcg_part_kernel<4>; break;
         case 8:  fn = (const void*)pcg_part_kernel<8>; break;
         case 16: fn = (const void*)pcg_part_kernel<16>; break;
         default: fn = (const void*)pcg_part_kernel<32>; break;
     }
     count_launch();
-    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(s->nblocks), dim3(s->nthreads), args, 0, (cudaStream_t)stream),
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(s->nblocks), dim3(s->nthreads), args, s->smem_bytes, (cudaStream_t)stream),
                       "pcg_part_kernel cooperative launch");
 }
 

@@ -608,6 +608,8 @@ class PartitionedSemiImplicitFEM:
         self._states_arr = L.ptr_array(self.states)
         self.info = torch.zeros(4, dtype=torch.int32, device=dev)
         self.blocks_per_grid = int(L.lib().pdx_pcg_part_blocks(h))
+        self.threads_per_block = int(L.lib().pdx_pcg_part_threads(h))
+        self.stage_slot_bytes = int(L.lib().pdx_pcg_part_stage_bytes(h))
 
     def __del__(self):
         try:

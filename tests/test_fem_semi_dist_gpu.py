@@ -96,8 +96,37 @@ def _oracle_steps(nsteps):
     return U, its
 
 
-@pytest.mark.parametrize('layout', ['sell', 'csr'])
-def test_one_rank_steps_match_oracle(cuda, layout):
+def test_copy_engine_staged_sell_product_matches_the_plain_one(cuda, monkeypatch):
+    """q = A p with the SELL slices staged through shared memory by cp.async.bulk (rows_dot_staged, the form large systems
+    run) against the per-thread loads.  The row products have the same accumulation order; the staged form runs other
+    block sizes, so the block partials of the dot products are added in another order: same iteration decisions, iterates
+    equal to the CG tolerance."""
+    from pdensorflow_b200.fem_dist import PartitionedSemiImplicitFEM
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    dims = (37, 29, 23)
+    n = dims[0] * dims[1] * dims[2]
+    rp, ci, kv, ml, mv = structured_tet_operator(*dims, H, SIGMA, 0, None, consistent_mass=True)
+    U0 = np.full(n, -80.0, dtype=np.float32)
+    U0[: 2 * dims[1] * dims[2]] = 20.0
+    out = {}
+    for stage in ('0', '1'):
+        monkeypatch.setenv('PDX_PCG_STAGE', stage)
+        fem = PartitionedSemiImplicitFEM(n, rp, ci, mv, kv, DT, math='exact', layout='sell')
+        fem.set_global_U(U0)
+        recs = []
+        for _ in range(12):
+            fem.step(1)
+            recs.append(fem.last_solve())
+        out[stage] = (fem.owned_U().cpu().numpy(), recs)
+    assert rel_l2(out['1'][0], out['0'][0]) <= TOL_CG
+    assert _same_iterations([r[0] for r in out['1'][1]], [r[0] for r in out['0'][1]])
+    assert all(r[2] == 0 for r in out['1'][1])
+    assert out['0'][0].max() > 0.0
+
+
+@pytest.mark.parametrize('layout,stage', [('sell', '0'), ('sell', '1'), ('csr', '0')])
+def test_one_rank_steps_match_oracle(cuda, layout, stage, monkeypatch):
+    monkeypatch.setenv('PDX_PCG_STAGE', stage)
     nsteps = 25
     Uo, its = _oracle_steps(nsteps)
     fem = _make(math='exact', layout=layout)
@@ -112,9 +141,10 @@ def test_one_rank_steps_match_oracle(cuda, layout):
     assert _same_iterations(got_its, its), (got_its, its)
 
 
-@pytest.mark.parametrize('world,layout', [(2, 'sell'), (3, 'sell'), (2, 'csr')])
-def test_ranks_sharing_one_gpu_match_one_rank(cuda, world, layout):
+@pytest.mark.parametrize('world,layout,stage', [(2, 'sell', '0'), (3, 'sell', '0'), (3, 'sell', '1'), (2, 'csr', '0')])
+def test_ranks_sharing_one_gpu_match_one_rank(cuda, world, layout, stage, monkeypatch):
     from pdensorflow_b200.fem_dist import PartitionedSemiImplicitFEM
+    monkeypatch.setenv('PDX_PCG_STAGE', stage)
     nsteps = 20
     ref = _make(math='exact', layout=layout)
     ref.set_global_U(_initial())

@@ -88,7 +88,8 @@ def main():
                           'algorithmic_gbs_per_gpu_iterations_only': round(n / world * it * bpi / ms / 1e6, 1),
                           'algorithmic_bytes_per_node_step': round(bps, 1),
                           'algorithmic_gbs_per_gpu': round(n / world * bps / ms / 1e6, 1),
-                          'cooperative_blocks': fem.blocks_per_grid, 'ghost_rows': [fem.glo, fem.ghi],
+                          'cooperative_blocks': fem.blocks_per_grid, 'threads_per_block': fem.threads_per_block,
+                          'sell_slices_staged_by_copy_engine': fem.stage_slot_bytes > 0, 'ghost_rows': [fem.glo, fem.ghi],
                           'setup_s_per_rank': round(setup, 1), 'finite': bool(torch.isfinite(fem.owned_U()).all())}), flush=True)
     if world > 1:
         dist.barrier()
