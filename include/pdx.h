@@ -268,6 +268,11 @@ int  pdx_pcg_solve_rhs0(pdx_pcg* s, const float* mval, const float* rhs0, float*
 /* Optional: tell the library the size of a CSR matrix once, when it is uploaded (the kernels pick their lanes-per-row
  * from nnz / n; without the hint pdx_fem_explicit_step uses 8 lanes - it never reads rowptr back). */
 int pdx_csr_hint(const int32_t* rowptr, int32_t n, int64_t nnz);
+/* Registers the widest slice (entries per row) of a SELL-32 matrix by its slice_ptr address (0 forgets it).  With it
+ * pdx_fem_explicit_step_sell / _sync run blocks of 10^6 rows and more on a persistent kernel that streams the slices
+ * through shared memory with the copy engine; without it (or for small blocks) the one-thread-per-row kernel runs.
+ * No device read at step time, so steps stay capturable. */
+int pdx_sell_hint(const int32_t* slice_ptr, int32_t max_width);
 
 /* Explicit mass-lumped FEM step named by the north star (no reference implementation;
  * SURVEY.md section 8a row E): U1 = U + dt*(dU + I0) - dt * mlinv * (K U), fused with the

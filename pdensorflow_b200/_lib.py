@@ -97,6 +97,7 @@ _SIGNATURES = {
     'pdx_pcg_solve': (C.c_int, [_P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P]),
     'pdx_pcg_solve_rhs0': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P]),
     'pdx_csr_hint': (C.c_int, [_P, C.c_int32, C.c_int64]),
+    'pdx_sell_hint': (C.c_int, [_P, C.c_int32]),
     'pdx_fem_explicit_step': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P, _P, _P,
                                         C.POINTER(_P), _P, C.c_float, _P]),
     'pdx_fem_explicit_step_part': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P, _P, _P, _P, _P,

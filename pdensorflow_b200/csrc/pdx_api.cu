@@ -30,6 +30,12 @@ int sm_count() {
 
 static std::mutex g_hint_mu;
 static std::unordered_map<const void*, int> g_hint;
+static std::unordered_map<const void*, int> g_sell_hint;
+int sell_width_hint(const int32_t* slice_ptr) {
+    std::lock_guard<std::mutex> lk(g_hint_mu);
+    auto it = g_sell_hint.find(slice_ptr);
+    return it == g_sell_hint.end() ? 0 : it->second;
+}
 int csr_group_hint(const int32_t* rowptr) {
     std::lock_guard<std::mutex> lk(g_hint_mu);
     auto it = g_hint.find(rowptr);
@@ -180,6 +186,14 @@ int pdx_csr_hint(const int32_t* rowptr, int32_t n, int64_t nnz) {
     std::lock_guard<std::mutex> lk(g_hint_mu);
     if (g_hint.size() > 256) g_hint.clear();
     g_hint[rowptr] = G;
+    return 0;
+}
+
+int pdx_sell_hint(const int32_t* slice_ptr, int32_t max_width) {
+    if (!slice_ptr || max_width < 0) { set_error("pdx_sell_hint: bad arguments"); return 1; }
+    std::lock_guard<std::mutex> lk(g_hint_mu);
+    if (g_sell_hint.size() > 256) g_sell_hint.clear();
+    if (max_width == 0) g_sell_hint.erase(slice_ptr); else g_sell_hint[slice_ptr] = max_width;
     return 0;
 }
 

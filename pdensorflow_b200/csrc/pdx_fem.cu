@@ -6,6 +6,7 @@
 // (conjgrad.py:172-203,257-312), JacobiPrecond.solve_precond_system (jacobi_precond.py:35-41).
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 #include "pdx_internal.h"
@@ -373,6 +374,7 @@ struct ExplArgs {
     unsigned int* ctrl;
     unsigned int* ctrl_lo;
     unsigned int* ctrl_hi;
+    int stage_slot_bytes;          // staged kernel: bytes of a ring slot (col + val words of the widest slice)
     int n_lo_ctas, n_hi_ctas;      // CTAs that hold rows < send_lo / >= n - send_hi (set by the launcher)
     int block_shift;               // SELL: CTA b works on row block (b + block_shift) % gridDim.x - the high edge first
     ModelParams mp;
@@ -513,8 +515,107 @@ __global__ void __launch_bounds__(256) fem_explicit_sell_kernel(const __grid_con
     expl_signal_neighbours(a, elo, ehi, pushed);
 }
 
+// The same step for LARGE blocks of rows: a persistent grid whose warps walk their slices with the matrix stream on the
+// copy engine (sell_rows_staged, pdx_fem_dev.cuh): the col / val words of the next slices are in flight while a warp
+// gathers and runs the ionic model - the plain kernel above waits for slice_ptr, then col / val, then the gathers
+// (0.88 of the HBM peak on config 5).  Every CTA holds rows of both edges: all of them take part in the neighbour flags.
+template <int MODEL, int MATH>
+__global__ void __launch_bounds__(512, 2) fem_explicit_sell_staged_kernel(const __grid_constant__ ExplArgs a) {
+    constexpr int NS = NStates<MODEL>::value;
+    extern __shared__ __align__(128) unsigned char dsm[];
+    sell_stage_init(dsm, a.stage_slot_bytes);
+    const bool elo = a.ctrl && a.ctrl_lo, ehi = a.ctrl && a.ctrl_hi;
+    expl_wait_neighbours(a, elo, ehi);
+    bool pushed = false;
+    unsigned int uses = 0;
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    sell_rows_staged(dsm, a.stage_slot_bytes, a.n, a.rowptr, a.col, a.kval, policy, uses,
+                     [&](int c) { return a.Uin[c]; },
+                     [&](int row, float ku) {
+        const size_t grow = (size_t)a.row_lo + row;
+        const float U = a.Uin[grow];
+        float st[PDX_MAX_STATES];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st[s] = a.st[s][row];
+        float dU = MODEL != PDX_MODEL_NONE ? ionic_update<MODEL, MATH>(U, st, a.mp) : 0.0f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) a.st[s][row] = st[s];
+        if (a.I0) dU += a.I0[row];
+        const float u1 = fmaf(-a.mp.dt * a.mlinv[row], ku, fmaf(a.mp.dt, dU, U));
+        a.Uout[grow] = u1;
+        if (a.mirror_lo && row < a.send_lo) { a.mirror_lo[grow] = u1; pushed = true; }
+        if (a.mirror_hi && row >= a.n - a.send_hi) { a.mirror_hi[grow] = u1; pushed = true; }
+    });
+    expl_signal_neighbours(a, elo, ehi, pushed);
+}
+
+// staged launch geometry for a slice width registered through pdx_sell_hint: threads, blocks, dynamic shared memory
+struct ExplStageGeom {
+    int threads, blocks;
+    size_t smem;
+};
+template <int MODEL, int MATH>
+bool expl_stage_geometry(int wmax, ExplStageGeom* g) {
+    static ExplStageGeom cache[PDX_MAX_DEVICES][64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PDX_MAX_DEVICES || wmax < 1 || wmax >= 64) return false;
+    ExplStageGeom& c = cache[dev][wmax];
+    if (c.threads == 0) {
+        c.threads = -1;
+        auto kern = fem_explicit_sell_staged_kernel<MODEL, MATH>;
+        const int slot = wmax * 256;
+        int smem_max = 0;
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
+            const int max_dyn = smem_max - (int)fa.sharedSizeBytes;
+            if (max_dyn > 0 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) == cudaSuccess) {
+                int best_warps = 0;
+                for (int cand : {512, 384, 256}) {
+                    const size_t need = sell_stage_smem_bytes(cand, slot);
+                    if (need > (size_t)max_dyn) continue;
+                    int blk = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blk, kern, cand, need) != cudaSuccess) continue;
+                    if (blk * cand / 32 > best_warps) {
+                        best_warps = blk * cand / 32;
+                        c.threads = cand; c.blocks = blk * sm_count(); c.smem = need;
+                    }
+                }
+                if (best_warps < 16) c.threads = -1;
+            }
+        }
+        cudaGetLastError();
+    }
+    if (c.threads <= 0) return false;
+    *g = c;
+    return true;
+}
+
 template <int MODEL, int MATH>
 int launch_expl_sell(const ExplArgs& a0, cudaStream_t s) {
+    // large row blocks whose slice width is known (pdx_sell_hint): persistent staged kernel.  PDX_EXPL_STAGE=0 / 1
+    // turn it off / force it for any size (A/B runs, tests).
+    {
+        const char* e = getenv("PDX_EXPL_STAGE");
+        const int mode = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2;
+        const int wmax = sell_width_hint(a0.rowptr);
+        ExplStageGeom g;
+        if (getenv("PDX_DEBUG")) fprintf(stderr, "[pdx] explicit sell: n %d wmax %d mode %d\n", a0.n, wmax, mode);
+        if (wmax > 0 && mode != 0 && (a0.n >= 1000000 || mode == 1) && ((uintptr_t)a0.col % 16) == 0 && ((uintptr_t)a0.kval % 16) == 0 &&
+            expl_stage_geometry<MODEL, MATH>(wmax, &g)) {
+            ExplArgs a = a0;
+            a.stage_slot_bytes = wmax * 256;
+            const int warps_needed = (a.n + 31) / 32;
+            int nb = g.blocks;
+            const int per_block = g.threads / 32;
+            if ((long long)nb * per_block > warps_needed) nb = (warps_needed + per_block - 1) / per_block;
+            a.n_lo_ctas = a.n_hi_ctas = nb;
+            fem_explicit_sell_staged_kernel<MODEL, MATH><<<(unsigned)nb, g.threads, g.smem, s>>>(a);
+            count_launch();
+            return check_cuda(cudaGetLastError(), "fem_explicit_sell_staged_kernel launch");
+        }
+    }
     ExplArgs a = a0;
     const int nb = (a.n + 255) / 256;
     if (a.ctrl) {

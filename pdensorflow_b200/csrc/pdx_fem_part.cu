@@ -285,79 +285,17 @@ __device__ __forceinline__ void rows_dot(const PartArgs& a, const Pol& pol, l2po
 // ahead in flight as cp.async.bulk copies (col and val words of a slice are contiguous: two copies, one mbarrier)
 // into a per-warp shared-memory ring; the lanes then read their columns from shared memory and have a whole row of
 // gathers in flight at once.  Products are accumulated in the same order as in rows_dot: same bits.
-constexpr int STAGE_NB = 2;
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 struct StageState {
     unsigned int uses;       // slots consumed so far by this warp (phase parity of the ring's mbarriers)
 };
 
+// the walker of pdx_fem_dev.cuh on this kernel's matrix, vector loads with their L2 policy
 template <class F>
 __device__ __forceinline__ void rows_dot_staged(const PartArgs& a, const Pol& pol, l2pol_t polx, const float* vals,
                                                 const float* xa, StageState& stg, F&& f) {
     extern __shared__ __align__(128) unsigned char dsm[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-    const int slot = a.stage_slot_bytes;
-    unsigned char* ring = dsm + (size_t)wib * STAGE_NB * slot;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + (size_t)nwb * STAGE_NB * slot) + wib * STAGE_NB;
-    int* widths = reinterpret_cast<int*>(dsm + (size_t)nwb * STAGE_NB * (slot + 8)) + wib * STAGE_NB;
-    const int gw = blockIdx.x * nwb + wib, nw = gridDim.x * nwb;
-    const int nsl = (a.n + 31) >> 5;
-    const int cnt = gw < nsl ? (nsl - gw + nw - 1) / nw : 0;          // slices gw, gw + nw, ... of this warp
-
-    auto issue = [&](int t, int beg, int end) {          // lane 0
-        const int sl = (int)((stg.uses + t) % STAGE_NB);
-        const uint32_t bytes = (uint32_t)(end - beg) * 4u;
-        const uint32_t bar = smem_addr(&bars[sl]);
-        widths[sl] = (end - beg) >> 5;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
-        const uint32_t dst = smem_addr(ring + (size_t)sl * slot);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                     ::"r"(dst), "l"(a.col + beg), "r"(bytes), "r"(bar), "l"(pol.mat) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                     ::"r"(dst + bytes), "l"(vals + beg), "r"(bytes), "r"(bar), "l"(pol.mat) : "memory");
-    };
-    if (lane == 0) {
-        for (int t = 0; t < STAGE_NB && t < cnt; ++t) {
-            const int s0 = gw + t * nw;
-            issue(t, a.rowptr[s0], a.rowptr[s0 + 1]);
-        }
-    }
-    for (int t = 0; t < cnt; ++t) {
-        int nbeg = 0, nend = 0;
-        const bool refill = lane == 0 && t + STAGE_NB < cnt;
-        if (refill) {                                    // slice_ptr of the refill: loaded now, used after the products
-            const int s1 = gw + (t + STAGE_NB) * nw;
-            nbeg = a.rowptr[s1]; nend = a.rowptr[s1 + 1];
-        }
-        const unsigned int use = stg.uses + t;
-        const int sl = (int)(use % STAGE_NB);
-        const uint32_t bar = smem_addr(&bars[sl]), parity = (use / STAGE_NB) & 1u;
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        const int w = widths[sl];
-        const int32_t* scol = reinterpret_cast<const int32_t*>(ring + (size_t)sl * slot) + lane;
-        const float* sval = reinterpret_cast<const float*>(ring + (size_t)sl * slot + (size_t)w * 128) + lane;
-        float acc = 0.0f;
-        int k = 0;
-        for (; k + 4 <= w; k += 4) {
-            const int c0 = scol[k * 32], c1 = scol[k * 32 + 32], c2 = scol[k * 32 + 64], c3 = scol[k * 32 + 96];
-            const float x0 = ldv(xa + c0, polx), x1 = ldv(xa + c1, polx), x2 = ldv(xa + c2, polx), x3 = ldv(xa + c3, polx);
-            acc = fmaf(sval[k * 32], x0, acc);
-            acc = fmaf(sval[k * 32 + 32], x1, acc);
-            acc = fmaf(sval[k * 32 + 64], x2, acc);
-            acc = fmaf(sval[k * 32 + 96], x3, acc);
-        }
-        for (; k < w; ++k) acc = fmaf(sval[k * 32], ldv(xa + scol[k * 32], polx), acc);
-        const int row = (gw + t * nw) * 32 + lane;
-        if (row < a.n) f(row, acc, 0.0f);
-        __syncwarp();                                    // every lane is done with the slot
-        if (refill) issue(t + STAGE_NB, nbeg, nend);
-    }
-    stg.uses += (unsigned int)cnt;
+    sell_rows_staged(dsm, a.stage_slot_bytes, a.n, a.rowptr, a.col, vals, pol.mat, stg.uses,
+                     [&](int c) { return ldv(xa + c, polx); }, [&](int row, float acc) { f(row, acc, 0.0f); });
 }
 
 // STAGED (G == 0 only): blocks of at most 512 threads with the shared-memory ring, 64 registers per thread
@@ -374,14 +312,7 @@ __global__ void __launch_bounds__(STAGED ? 512 : 1024, 2) pcg_part_kernel(const 
     StageState stg{0u};
     if constexpr (STAGED) {
         extern __shared__ __align__(128) unsigned char dsm[];
-        const int nwb = blockDim.x >> 5, wib = threadIdx.x >> 5;
-        uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + (size_t)nwb * STAGE_NB * a.stage_slot_bytes) + wib * STAGE_NB;
-        if ((threadIdx.x & 31) == 0) {
-            for (int i = 0; i < STAGE_NB; ++i)
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[i])) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
+        sell_stage_init(dsm, a.stage_slot_bytes);
     }
     Pol pol;
     pol.mat  = l2_policy(a.keep & 32 ? 2 : 0);
@@ -643,7 +574,7 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
                 if (cudaFuncGetAttributes(&fa, pcg_part_kernel<0, true>) == cudaSuccess) max_dyn = smem_max - (int)fa.sharedSizeBytes;
                 if (max_dyn > 0 && cudaFuncSetAttribute(pcg_part_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) == cudaSuccess) {
                     for (int cand : {512, 384, 256}) {
-                        const size_t need = (size_t)(cand / 32) * STAGE_NB * ((size_t)slot + 8 + 4) + 128;
+                        const size_t need = sell_stage_smem_bytes(cand, slot);
                         if (need > (size_t)max_dyn) continue;
                         int blk = 0;
                         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blk, pcg_part_kernel<0, true>, cand, need) != cudaSuccess) continue;

@@ -63,6 +63,7 @@ void set_error(const std::string& msg);
 int  check_cuda(cudaError_t e, const char* what);
 void count_launch(int64_t n = 1);
 int  sm_count();                       // multiprocessors of the current device (cached per ordinal)
+int  sell_width_hint(const int32_t* slice_ptr);   // widest slice registered through pdx_sell_hint, or 0
 int  csr_group_hint(const int32_t* rowptr);   // lanes per row registered through pdx_csr_hint, or 0
 
 void fill_model_params(int model, const float* params, float dt, ModelParams* out);

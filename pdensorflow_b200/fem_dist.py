@@ -104,6 +104,8 @@ def csr_to_sell32_device(rowptr, col, val, row_lo=0):
         sval = torch.empty(total, dtype=torch.float32, device=rowptr.device)
         L.check(lib.pdx_sell_fill(n, int(row_lo), L.ptr(rowptr), L.ptr(col), L.ptr(val), L.ptr(sp32), L.ptr(scol),
                                   L.ptr(sval), L.stream_ptr()))
+        # widest slice: lets the explicit step stream large matrices through shared memory (pdx_sell_hint)
+        L.check(lib.pdx_sell_hint(L.ptr(sp32), int(widths[:nsl].max()) if nsl else 0))
     return sp32, scol, sval
 
 
@@ -291,6 +293,13 @@ class PartitionedExplicitFEM:
         self._cur = 0
         self._primed = world == 1 or self._local
         self.nsteps_done = 0
+
+    def __del__(self):
+        try:        # the slice-width hint is keyed by the slice_ptr address: forget it with the matrix
+            if getattr(self, 'layout', None) == 'sell' and getattr(self, 'rowptr', None) is not None:
+                L.lib().pdx_sell_hint(L.ptr(self.rowptr), 0)
+        except Exception:
+            pass
 
     # ---- exchange planning --------------------------------------------------------------------
     def _gather_ghosts(self, group):

@@ -80,6 +80,33 @@ def _worker(rank, world, port, nsteps, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('world', [1, 3])
+def test_copy_engine_staged_explicit_step_is_bitwise_the_plain_one(cuda, world, monkeypatch):
+    """The persistent kernel that streams the SELL slices through shared memory (the form blocks of 10^6 rows and more
+    run; forced here) against the one-thread-per-row kernel: same accumulation order per row, bitwise equal - alone and
+    with three row blocks sharing one GPU (ghost stores + neighbour flags from the persistent grid)."""
+    from pdensorflow_b200.fem_dist import PartitionedExplicitFEM, row_blocks
+    from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator
+    dims = (31, 17, 19)
+    n = dims[0] * dims[1] * dims[2]
+    out = {}
+    for stage in ('0', '1'):
+        monkeypatch.setenv('PDX_EXPL_STAGE', stage)
+        ranks = []
+        for r, (lo, hi) in enumerate(row_blocks(n, world)):
+            rp, ci, kv, ml = structured_tet_operator(*dims, H, SIGMA, lo, hi)
+            ranks.append(PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=r, world=world,
+                                                connect=world == 1))
+        if world > 1:
+            PartitionedExplicitFEM.connect_local(ranks)
+        for f in ranks:
+            f.set_global_U(_initial(n, dims))
+        PartitionedExplicitFEM.step_local(ranks, 30)
+        torch.cuda.synchronize()
+        out[stage] = np.concatenate([f.owned_U().cpu().numpy() for f in ranks])
+    assert np.array_equal(out['0'], out['1']) and out['0'].max() > 0.0
+
+
 def test_graph_replayed_blocks_equal_single_steps(cuda):
     from pdensorflow_b200.fem_dist import PartitionedExplicitFEM
     from pdensorflow_b200.gpuSolve.entities.synthetic import structured_tet_operator

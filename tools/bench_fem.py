@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--skip-config1', action='store_true')
     ap.add_argument('--layout', default='sell', choices=['sell', 'csr'])
     ap.add_argument('--sync', default='auto', choices=['auto', 'flags', 'barrier'])
+    ap.add_argument('--ab-stage', action='store_true', help='A/B in ONE process: the one-thread-per-row kernel and the copy-engine staged kernel, alternating')
     ap.add_argument('--no-graph', action='store_true', help='one Python launch per step instead of graph replays of 10 steps')
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
@@ -48,6 +49,21 @@ def main():
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.ab_stage and world == 1:
+        res = {'0': [], '2': []}
+        for rep in range(4):
+            for mode in ('0', '2'):
+                os.environ['PDX_EXPL_STAGE'] = mode
+                fem.step(10)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                fem.step(args.steps)
+                a1.record()
+                torch.cuda.synchronize()
+                res[mode].append(round(a0.elapsed_time(a1) / args.steps, 4))
+        print(json.dumps({'ab_ms_per_step': {'thread_per_row': res['0'], 'copy_engine_staged': res['2']}, 'nodes': n}), flush=True)
+        return
     advance = fem.step if args.no_graph else fem.run
     advance(20)
     torch.cuda.synchronize()
