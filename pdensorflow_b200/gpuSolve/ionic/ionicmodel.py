@@ -64,6 +64,7 @@ class IonicModel:
         """If ``pname`` exists, set it to ``pvalue`` (scalar or per-node array)."""
         internal_name = '_{}'.format(pname)
         self._pb_cache = None
+        self._param_version = getattr(self, '_param_version', 0) + 1     # invalidates graph-captured steps
         if internal_name in self.__dict__.keys():
             if np.ndim(pvalue) == 0 or np.size(pvalue) == 1:
                 setattr(self, internal_name, torch.tensor(float(np.float32(np.asarray(pvalue).reshape(-1)[0])),

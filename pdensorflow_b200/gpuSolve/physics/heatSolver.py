@@ -29,6 +29,7 @@ class HeatSolver:
         self._Tend = 10
         self._use_renumbering = False
         self._explicit_lumped = False     # opt-in (not in the reference): explicit mass-lumped step
+        self._graph_steps = True          # (not in the reference) replay a time step as a CUDA graph once its shape is known
         self._device_assembly = None      # None: on the device above DEVICE_ASSEMBLY_MIN_ELEMENTS elements; True / False
         if cfgdict is not None:
             for attribute in list(self.__dict__.keys()):
@@ -48,6 +49,7 @@ class HeatSolver:
         self._StimulusDict = None
         self._nt = int(self._Tend // self._dt)
         self._I0_cache = {}
+        self._step_graphs = {}
         self._rhs0 = None
         self._rhs = None
         self._perm_d = None
@@ -172,12 +174,53 @@ class HeatSolver:
             self._I0_cache[k] = I0
         return I0
 
+    # ---- CUDA-graph replay of a time step ------------------------------------------------------
+    # The reference's loop calls step(t) once per time step (Tests/FEM/Fenton/fenton.py:119-132); on a 63 001-node mesh
+    # the two kernels of a step take ~0.06-0.08 ms on the device, about what Python needs to prepare and enqueue them.
+    # A step is fully described by (potential buffer, forcing field, ionic parameters, solver settings): the first step
+    # with a given description runs eagerly (allocations, caches), the second is captured into a CUDA graph, every later
+    # one is a single graph launch.  cfg key ``graph_steps`` (default True) / PDX_STEP_GRAPH=0 turn it off.
+    def _step_token(self):
+        return (int(self._Solver.maxiter()), float(self._Solver.toll()), float(self._dt))
+
+    def _graph_step(self, I0):
+        import os
+        if os.environ.get('PDX_STEP_GRAPH', '1') == '0' or torch.cuda.is_current_stream_capturing():
+            return self.solve_step(self._U, I0)
+        key = (self._U.data_ptr(), I0.data_ptr(), self._step_token())
+        ent = self._step_graphs.get(key)
+        if ent is None:                                   # first visit: eager
+            if len(self._step_graphs) > 16:
+                self._step_graphs.clear()
+            self._step_graphs[key] = 'seen'
+            return self.solve_step(self._U, I0)
+        if ent == 'eager':
+            return self.solve_step(self._U, I0)
+        if ent == 'seen':                                 # second visit: capture (executes nothing), then replay
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        out = self.solve_step(self._U, I0)
+            except Exception:
+                torch.cuda.synchronize()
+                self._step_graphs[key] = 'eager'          # e.g. a launch kind the driver cannot capture
+                return self.solve_step(self._U, I0)
+            cur.wait_stream(side)
+            ent = (g, out, self._U, I0)                   # the graph reads / writes these tensors: keep them alive
+            self._step_graphs[key] = ent
+        ent[0].replay()
+        return ent[1]
+
     def step(self, t):
         """Advance one time step; t is the absolute simulation time at the end of the step."""
         if not self._ready_for_run:
             raise Exception("model not initialised for run!")
         I0 = self._compute_forcing(t)
-        U1 = self.solve_step(self._U, I0)
+        U1 = self._graph_step(I0) if self._graph_steps else self.solve_step(self._U, I0)
         self._U = U1
         self._ctime = t
         return self._U

@@ -84,6 +84,11 @@ class MonodomainSolver(HeatSolver):
                 self._materials.remove_all_nodal_properties()
         self._ready_for_run = True
 
+    def _step_token(self):
+        m = self._ionic_model
+        return super()._step_token() + (id(m), getattr(m, '_param_version', 0), float(m._dt), getattr(m, 'math_mode', None),
+                                        bool(self._explicit_lumped))
+
     # ---- per-step kernel ----------------------------------------------------
     def solve_step(self, U, I0):
         m = self._ionic_model
