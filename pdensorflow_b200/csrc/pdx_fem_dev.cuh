@@ -100,10 +100,13 @@ __device__ __forceinline__ void sell_stage_init(unsigned char* dsm, int slot_byt
 
 // uses: slots this warp has consumed so far (carries the mbarrier phase from call to call).  ldx(c) returns x[c];
 // f(row, A_row . x) is called by the lane that owns the row.  policy: L2 cache policy of the matrix stream.
-template <class LDX, class F>
+// pre(slice) / post(slice): called by every lane of the warp right before the gathers of a slice and right after its
+// rows are done (hooks for the neighbour flags of a partitioned step).
+// smap(v): the slice visited v-th (a permutation of 0 .. nsl-1; identity unless the caller wants an order).
+template <class LDX, class F, class PRE, class POST, class SMAP>
 __device__ __forceinline__ void sell_rows_staged(unsigned char* dsm, int slot_bytes, int n, const int32_t* slice_ptr,
                                                  const int32_t* col, const float* vals, unsigned long long policy,
-                                                 unsigned int& uses, LDX&& ldx, F&& f) {
+                                                 unsigned int& uses, LDX&& ldx, F&& f, PRE&& pre, POST&& post, SMAP&& smap) {
     constexpr int NB = SELL_STAGE_NB;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     unsigned char* ring = dsm + (size_t)wib * NB * slot_bytes;
@@ -128,7 +131,7 @@ __device__ __forceinline__ void sell_rows_staged(unsigned char* dsm, int slot_by
     };
     if (lane == 0) {
         for (int t = 0; t < NB && t < cnt; ++t) {
-            const int s0 = gw + t * nw;
+            const int s0 = smap(gw + t * nw);
             issue(t, slice_ptr[s0], slice_ptr[s0 + 1]);
         }
     }
@@ -136,7 +139,7 @@ __device__ __forceinline__ void sell_rows_staged(unsigned char* dsm, int slot_by
         int nbeg = 0, nend = 0;
         const bool refill = lane == 0 && t + NB < cnt;
         if (refill) {                                    // slice_ptr of the refill: loaded now, used after the products
-            const int s1 = gw + (t + NB) * nw;
+            const int s1 = smap(gw + (t + NB) * nw);
             nbeg = slice_ptr[s1]; nend = slice_ptr[s1 + 1];
         }
         const unsigned int use = uses + t;
@@ -146,6 +149,8 @@ __device__ __forceinline__ void sell_rows_staged(unsigned char* dsm, int slot_by
         while (!done)
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        const int slice = smap(gw + t * nw);
+        pre(slice);
         const int w = widths[sl];
         const int32_t* scol = reinterpret_cast<const int32_t*>(ring + (size_t)sl * slot_bytes) + lane;
         const float* sval = reinterpret_cast<const float*>(ring + (size_t)sl * slot_bytes + (size_t)w * 128) + lane;
@@ -160,12 +165,21 @@ __device__ __forceinline__ void sell_rows_staged(unsigned char* dsm, int slot_by
             acc = fmaf(sval[k * 32 + 96], x3, acc);
         }
         for (; k < w; ++k) acc = fmaf(sval[k * 32], ldx(scol[k * 32]), acc);
-        const int row = (gw + t * nw) * 32 + lane;
+        const int row = slice * 32 + lane;
         if (row < n) f(row, acc);
+        post(slice);
         __syncwarp();                                    // every lane is done with the slot
         if (refill) issue(t + NB, nbeg, nend);
     }
     uses += (unsigned int)cnt;
+}
+
+template <class LDX, class F>
+__device__ __forceinline__ void sell_rows_staged(unsigned char* dsm, int slot_bytes, int n, const int32_t* slice_ptr,
+                                                 const int32_t* col, const float* vals, unsigned long long policy,
+                                                 unsigned int& uses, LDX&& ldx, F&& f) {
+    sell_rows_staged(dsm, slot_bytes, n, slice_ptr, col, vals, policy, uses, ldx, f, [](int) {}, [](int) {},
+                     [](int v) { return v; });
 }
 
 // grid_total of two partial arrays in one pass

@@ -656,7 +656,9 @@ int pdx_pcg_part_create(const pdx_pcg_part_desc* d, void* const* peer_ws, int32_
         int l2bytes = 0;
         cudaDeviceGetAttribute(&l2bytes, cudaDevAttrL2CacheSize, dev);
         const double budget = 0.75 * (double)l2bytes, vec_bytes = 4.0 * (double)window;
-        int keep = 32, nfit = vec_bytes > 0 ? (int)(budget / vec_bytes) : 5;
+        // evict-first only for a matrix that cannot stay in the L2 anyway: a 5e5-row block (60 MB of col / val words, what
+        // a rank of a strong-scaled solve holds) is L2 resident across iterations and must not be pushed out
+        int keep = 8.0 * (double)s->nnz > (double)l2bytes ? 32 : 0, nfit = vec_bytes > 0 ? (int)(budget / vec_bytes) : 5;
         static const int order[5] = {1, 2, 4, 8, 16};
         for (int i = 0; i < 5 && i < nfit; ++i) keep |= order[i];
         if (const char* e = getenv("PDX_PCG_L2KEEP")) keep = atoi(e);
