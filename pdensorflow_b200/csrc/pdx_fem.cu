@@ -524,12 +524,11 @@ __global__ void __launch_bounds__(512, 2) fem_explicit_sell_staged_kernel(const 
     constexpr int NS = NStates<MODEL>::value;
     extern __shared__ __align__(128) unsigned char dsm[];
     sell_stage_init(dsm, a.stage_slot_bytes);
-    // Neighbour flags per SLICE, edge slices LAST: the warps walk the interior slices first and the slices that hold
-    // edge rows at the end of the kernel.  A warp waits for a neighbour right before its first edge slice - by then the
-    // neighbour, which finished ITS previous step about when this rank did, has long published it - and every finished
-    // edge slice counts towards this rank's publication, which the neighbours need only at the end of their own next
-    // kernel: both directions have a whole kernel of slack, back-to-back (graph replayed) steps never spin.  (Edge slices
-    // first, or all CTAs waiting at the start, measured SLOWER than a barrier per step on 8 GPUs: 0.083 / 0.080 vs 0.077 ms.)
+    // Neighbour flags per SLICE (opt-in, sync='flags'): a warp waits for a neighbour right before its first slice that
+    // holds edge rows, every finished edge slice counts towards this rank's publication.  Slices are dealt out round robin,
+    // so the low edge comes first and the high edge last for every warp.  Measured on 8 GPUs (config 5, 2.5 M rows each):
+    // 0.083 ms per step, edge slices walked last 0.090, all CTAs waiting at the start 0.080 - against 0.076-0.077 with a
+    // barrier between steps, which therefore stays the default of PartitionedExplicitFEM.
     const bool flo = a.ctrl && a.ctrl_lo, fhi = a.ctrl && a.ctrl_hi;
     const int lo_slices = (a.send_lo + 31) >> 5;                 // slices [0, lo_slices) hold rows < send_lo
     const int hi_first = (a.n - a.send_hi) >> 5;                 // slices [hi_first, nsl) hold rows >= n - send_hi
@@ -598,13 +597,7 @@ __global__ void __launch_bounds__(512, 2) fem_explicit_sell_staged_kernel(const 
             }
         }
     },
-                     [&](int v) {           // visiting order: interior slices, then the low edge, then the high edge
-        const int n_int = hi_first - lo_slices;
-        if (!(flo || fhi) || n_int <= 0) return v;
-        if (v < n_int) return lo_slices + v;
-        const int e = v - n_int;
-        return e < lo_slices ? e : hi_first + (e - lo_slices);
-    });
+                     [](int v) { return v; });
 }
 
 // staged launch geometry for a slice width registered through pdx_sell_hint: threads, blocks, dynamic shared memory

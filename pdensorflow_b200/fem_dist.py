@@ -222,9 +222,11 @@ class PartitionedExplicitFEM:
         if exchange not in ('auto', 'band', 'lists'):
             raise ValueError("exchange must be 'auto', 'band' or 'lists'")
         self.exchange = exchange
-        # sync: 'flags' = the step kernels order themselves through neighbour flags in peer memory
-        # (pdx_fem_explicit_step_sync, band exchange only); 'barrier' = one symmetric-memory barrier per step;
-        # 'auto' = flags whenever the exchange is the band form
+        # sync: 'barrier' = one symmetric-memory barrier per step (default, 'auto'); 'flags' = the step kernels order
+        # themselves through neighbour flags in peer memory (pdx_fem_explicit_step_sync, band exchange only; steps are
+        # then graph replayable).  Measured on config 5: level on 2 GPUs (0.0756 vs 0.0766 ms per step at 2.5 M rows
+        # each), SLOWER on 8 (0.083-0.090 vs 0.076-0.077: the system-scope fences and flag words of 2 x 2312 edge slices
+        # per step cost more than the ~6 us barrier) - hence opt-in
         if sync not in ('auto', 'flags', 'barrier'):
             raise ValueError("sync must be 'auto', 'flags' or 'barrier'")
         self.sync = sync
@@ -272,7 +274,7 @@ class PartitionedExplicitFEM:
             self._peer_lo = self._peer_hi = [None, None]
         for b in self.U:
             b.fill_(-80.0 if self.model_id != L.MODEL_NONE else 0.0)
-        if self._hdl is not None and self.exchange == 'band' and self.sync in ('auto', 'flags'):
+        if self._hdl is not None and self.exchange == 'band' and self.sync == 'flags':
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
             self._ctrl = symm.empty((32,), dtype=torch.int32, device=dev)
@@ -344,7 +346,7 @@ class PartitionedExplicitFEM:
             if f.exchange == 'lists':
                 f._peer_lo = f._peer_hi = [None, None]
                 f._install_push([[g.U[b].data_ptr() for g in ranks] for b in range(2)])
-        if all(f.exchange == 'band' and f.sync in ('auto', 'flags') for f in ranks):
+        if all(f.exchange == 'band' and f.sync == 'flags' for f in ranks):
             # the neighbour-flag protocol on one GPU: the ranks share a stream, so a waiting kernel's neighbours have
             # always finished already - the flags are exercised, never contended
             for f in ranks:

@@ -66,9 +66,10 @@ def _worker(rank, world, port, nsteps, q):
         n = nx * ny * nz
         lo, hi = row_blocks(n, world)[rank]
         rp, ci, kv, ml = structured_tet_operator(nx, ny, nz, H, SIGMA, lo, hi)
-        fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=rank, world=world)
+        fem = PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=rank, world=world,
+                                     sync='flags' if rank >= 0 and world % 2 == 0 else 'barrier')
         assert (fem.send_lo > 0) == (rank > 0) and (fem.send_hi > 0) == (rank < world - 1)
-        assert fem.sync == 'flags'          # band exchange: the step kernels order themselves through neighbour flags
+        assert fem.sync == ('flags' if world % 2 == 0 else 'barrier')     # both orderings are exercised (2 / 3 ranks)
         fem.set_global_U(_initial(n, DIMS))
         fem.step(nsteps // 2)
         fem.set_global_U(fem_gather(fem, dist, world))      # re-install mid-run: flags keep counting across it
@@ -96,7 +97,7 @@ def test_copy_engine_staged_explicit_step_is_bitwise_the_plain_one(cuda, world, 
         for r, (lo, hi) in enumerate(row_blocks(n, world)):
             rp, ci, kv, ml = structured_tet_operator(*dims, H, SIGMA, lo, hi)
             ranks.append(PartitionedExplicitFEM(n, rp, ci, kv, ml, DT, model='fenton4v', math='exact', rank=r, world=world,
-                                                connect=world == 1))
+                                                connect=world == 1, sync='flags' if world > 1 else 'auto'))
         if world > 1:
             PartitionedExplicitFEM.connect_local(ranks)
         for f in ranks:
