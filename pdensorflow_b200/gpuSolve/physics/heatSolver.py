@@ -181,7 +181,9 @@ class HeatSolver:
     # with a given description runs eagerly (allocations, caches), the second is captured into a CUDA graph, every later
     # one is a single graph launch.  cfg key ``graph_steps`` (default True) / PDX_STEP_GRAPH=0 turn it off.
     def _step_token(self):
-        return (int(self._Solver.maxiter()), float(self._Solver.toll()), float(self._dt))
+        # everything a captured step froze besides the buffers: solver settings and the matrices behind the handles
+        return (int(self._Solver.maxiter()), float(self._Solver.toll()), float(self._dt), id(self._MASS), id(self._STIFFNESS),
+                id(getattr(self._Solver, '_A', None)), id(getattr(self._Solver, '_handle', None)), id(getattr(self._Solver, '_part', None)))
 
     def _graph_step(self, I0):
         import os
