@@ -25,6 +25,7 @@
 //
 // Algorithmic bytes per node-step with Fenton-Karma: 6 x 4 (tensor) + 32 (U,V,W,S read + written) = 56.
 #include <cstdlib>
+#include <type_traits>
 #include "pdx_internal.h"
 #include "pdx_tma.cuh"
 
@@ -200,10 +201,28 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
 
     const int srow = trow * TZ + N * zl;
 
-    for (int i = 0; i < np; ++i) {
+    // ---- the march.  The rows of the three planes in use live in REGISTERS and rotate with the march (r02b): a plane's
+    // rows j-1, j, j+1 of U (with their z neighbours), C00, C01 (rows j-1, j+1) and C02 are read from shared memory ONCE,
+    // when the plane arrives, and serve as plane i+1, then i, then i-1 - 27 shared-memory loads per thread and plane
+    // instead of 44 (ncu of the first version: short_scoreboard / mio_throttle led at one CTA per SM).  The loop is
+    // unrolled by three so that the rotation is a renaming of registers, not a copy.
+    W xw[3][3];            // [plane slot][row j-1, j, j+1]: U0, z-edge patched
+    V c00[3];              // [plane slot] row j
+    V c01[3][2];           // [plane slot][row j-1, j+1]
+    W c02[3];              // [plane slot] row j with z neighbours
+    auto load_plane = [&](auto slot_c, int j) {       // logical plane j (already waited for) -> register slot
+        constexpr int SL = decltype(slot_c)::value;
+        const float* Uj = slot(j, F_U);
+        xw[SL][0] = ldw<N>(Uj + rm); xw[SL][1] = ldw<N>(Uj + rc); xw[SL][2] = ldw<N>(Uj + rp);
+        c00[SL] = ldv_s<N>(slot(j, F_C00) + cc);
+        c01[SL][0] = ldv_s<N>(slot(j, F_C01) + cm); c01[SL][1] = ldv_s<N>(slot(j, F_C01) + cp);
+        c02[SL] = ldw<N>(slot(j, F_C02) + cc);
+        if (zb_tile) { fixXw(xw[SL][0]); fixXw(xw[SL][1]); fixXw(xw[SL][2]); fixCw(c02[SL]); }
+    };
+    auto body = [&](auto role, int i) {
+        constexpr int SM_ = decltype(role)::value, SC_ = (SM_ + 1) % 3, SP_ = (SM_ + 2) % 3;   // slots of planes i-1, i, i+1
         const int p = xb + i;
         const int jc = i + 1;
-        if (i == 0) { wait_plane(0); wait_plane(1); }
         wait_plane(i + 2);
         V stc[NS > 0 ? NS : 1];
         if (NS > 0) {
@@ -211,36 +230,28 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
 #pragma unroll
             for (int s = 0; s < NS; ++s) stc[s] = ldv_s<N>(sslot(i, s) + srow);
         }
-
         if (act) {
             const size_t gi = ((size_t)p * a.ny + gy) * a.nz + z;
-            const float* Um = slot(jc - 1, F_U);
+            load_plane(std::integral_constant<int, SP_>{}, jc + 1);
+            const W& x_mc = xw[SM_][1]; const W& x_pc = xw[SP_][1];
+            const W& x_cm = xw[SC_][0]; const W& x_cc = xw[SC_][1]; const W& x_cp = xw[SC_][2];
+            const W& x_mm = xw[SM_][0]; const W& x_mp = xw[SM_][2]; const W& x_pm = xw[SP_][0]; const W& x_pp = xw[SP_][2];
             const float* Uc = slot(jc, F_U);
-            const float* Up = slot(jc + 1, F_U);
-            // ---- potential ----
-            W x_mc = ldw<N>(Um + rc), x_pc = ldw<N>(Up + rc);                        // planes i-1 / i+1, row j
-            W x_cm = ldw<N>(Uc + rm), x_cc = ldw<N>(Uc + rc), x_cp = ldw<N>(Uc + rp);   // plane i, rows j-1, j, j+1
-            V x_mm = ldv_s<N>(Um + rm), x_mp = ldv_s<N>(Um + rp), x_pm = ldv_s<N>(Up + rm), x_pp = ldv_s<N>(Up + rp);
             V raw;
 #pragma unroll
             for (int e = 0; e < N; ++e) raw.v[e] = x_cc.v[e + 1];
             if (MODEL != PDX_MODEL_NONE) {
                 if (p < a.xclo || p > a.xchi) raw = ldv_s<N>(a.Uin + gi);     // CTA uniform, two planes of the grid
-                else if (row_clamped) raw = ldv_s<N>(Uc + cc);                // rows 0 and ny-1: the halo row of the tile
+                else if (row_clamped || zb_tile) raw = ldv_s<N>(Uc + cc);     // the unclamped row, z edges unpatched
             }
-            if (zb_tile) {
-                fixXw(x_mc); fixXw(x_pc); fixXw(x_cm); fixXw(x_cc); fixXw(x_cp);
-                fixXv(x_mm); fixXv(x_mp); fixXv(x_pm); fixXv(x_pp);
-            }
-            // ---- tensor ----
-            const V c00m = ldv_s<N>(slot(jc - 1, F_C00) + cc), c00c = ldv_s<N>(slot(jc, F_C00) + cc), c00p = ldv_s<N>(slot(jc + 1, F_C00) + cc);
+            // ---- tensor components that are only read in the centre plane ----
             const V c11m = ldv_s<N>(slot(jc, F_C11) + cm), c11c = ldv_s<N>(slot(jc, F_C11) + cc), c11p = ldv_s<N>(slot(jc, F_C11) + cp);
             W c22 = ldw<N>(slot(jc, F_C22) + cc);
-            const V c01mm = ldv_s<N>(slot(jc - 1, F_C01) + cm), c01mp = ldv_s<N>(slot(jc - 1, F_C01) + cp);
-            const V c01pm = ldv_s<N>(slot(jc + 1, F_C01) + cm), c01pp = ldv_s<N>(slot(jc + 1, F_C01) + cp);
-            W c02m = ldw<N>(slot(jc - 1, F_C02) + cc), c02p = ldw<N>(slot(jc + 1, F_C02) + cc);
             W c12m = ldw<N>(slot(jc, F_C12) + cm), c12p = ldw<N>(slot(jc, F_C12) + cp);
-            if (zb_tile) { fixCw(c22); fixCw(c02m); fixCw(c02p); fixCw(c12m); fixCw(c12p); }
+            if (zb_tile) { fixCw(c22); fixCw(c12m); fixCw(c12p); }
+            const V& c00m = c00[SM_]; const V& c00c = c00[SC_]; const V& c00p = c00[SP_];
+            const V& c01mm = c01[SM_][0]; const V& c01mp = c01[SM_][1]; const V& c01pm = c01[SP_][0]; const V& c01pp = c01[SP_][1];
+            const W& c02m = c02[SM_]; const W& c02p = c02[SP_];
 
             V out;
 #pragma unroll
@@ -249,17 +260,17 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
                 const float x0 = x_cc.v[k1];
                 // axis x, side +/-: normal, transverse y, transverse z     (:50-62)
                 float tp = t_main<MATH>(c00p.v[e], c00c.v[e], x_pc.v[k1], x0, hx, rhx);
-                tp = madd<MATH>(tp, t_cross<MATH>(c01pp.v[e], c01pm.v[e], x_pp.v[e], x_pm.v[e], hy, rhy));
+                tp = madd<MATH>(tp, t_cross<MATH>(c01pp.v[e], c01pm.v[e], x_pp.v[k1], x_pm.v[k1], hy, rhy));
                 tp = madd<MATH>(tp, t_cross<MATH>(c02p.v[k2], c02p.v[k0], x_pc.v[k2], x_pc.v[k0], hz, rhz));
                 float tm = t_main<MATH>(c00m.v[e], c00c.v[e], x_mc.v[k1], x0, hx, rhx);
-                tm = madd<MATH>(tm, t_cross<MATH>(c01mp.v[e], c01mm.v[e], x_mp.v[e], x_mm.v[e], hy, rhy));
+                tm = madd<MATH>(tm, t_cross<MATH>(c01mp.v[e], c01mm.v[e], x_mp.v[k1], x_mm.v[k1], hy, rhy));
                 tm = madd<MATH>(tm, t_cross<MATH>(c02m.v[k2], c02m.v[k0], x_mc.v[k2], x_mc.v[k0], hz, rhz));
                 const float gx = mdivh<MATH>(msub<MATH>(mmul<MATH>(0.5f, tp), mmul<MATH>(-0.5f, tm)), hx, rhx);
                 // axis y: transverse x, normal, transverse z               (:64-76)
-                float up = t_cross<MATH>(c01pp.v[e], c01mp.v[e], x_pp.v[e], x_mp.v[e], hx, rhx);
+                float up = t_cross<MATH>(c01pp.v[e], c01mp.v[e], x_pp.v[k1], x_mp.v[k1], hx, rhx);
                 up = madd<MATH>(up, t_main<MATH>(c11p.v[e], c11c.v[e], x_cp.v[k1], x0, hy, rhy));
                 up = madd<MATH>(up, t_cross<MATH>(c12p.v[k2], c12p.v[k0], x_cp.v[k2], x_cp.v[k0], hz, rhz));
-                float um = t_cross<MATH>(c01pm.v[e], c01mm.v[e], x_pm.v[e], x_mm.v[e], hx, rhx);
+                float um = t_cross<MATH>(c01pm.v[e], c01mm.v[e], x_pm.v[k1], x_mm.v[k1], hx, rhx);
                 um = madd<MATH>(um, t_main<MATH>(c11m.v[e], c11c.v[e], x_cm.v[k1], x0, hy, rhy));
                 um = madd<MATH>(um, t_cross<MATH>(c12m.v[k2], c12m.v[k0], x_cm.v[k2], x_cm.v[k0], hz, rhz));
                 const float gyv = mdivh<MATH>(msub<MATH>(mmul<MATH>(0.5f, up), mmul<MATH>(-0.5f, um)), hy, rhy);
@@ -296,6 +307,19 @@ fd_aniso_kernel(const __grid_constant__ AnisoMaps maps, const __grid_constant__ 
             if (i + STAGES < nlog) issue(i + STAGES);
             if (NS > 0 && i + SSTAGES < np) issue_states(i + SSTAGES);
         }
+    };
+    if (np > 0) {
+        wait_plane(0);
+        wait_plane(1);
+        if (act) {
+            load_plane(std::integral_constant<int, 0>{}, 0);
+            load_plane(std::integral_constant<int, 1>{}, 1);
+        }
+    }
+    for (int i = 0; i < np; i += 3) {
+        body(std::integral_constant<int, 0>{}, i);
+        if (i + 1 < np) body(std::integral_constant<int, 1>{}, i + 1);
+        if (i + 2 < np) body(std::integral_constant<int, 2>{}, i + 2);
     }
 }
 
@@ -342,8 +366,8 @@ int launch_inst(const FdArgs& a0, const AnisoMaps& m, cudaStream_t s) {
 template <int MODEL>
 int launch_math(int math, const FdArgs& a, const AnisoMaps& m, cudaStream_t s) {
     // nodes per thread (PDX_ANISO_NPT=4|2 overrides).  Measured on 256 x 512^2 FK (profiles/r02_aniso_throughput.jsonl):
-    // FAST 85.4 Gnode-steps/s with 4 against 84.1 with 2 (heat 124 / 113); EXACT (IEEE divisions: issue bound) 8.3
-    // against 13.4 - more warps pay only there.
+    // FAST 97.5 Gnode-steps/s with 4 and with 2 alike; EXACT (IEEE divisions: issue bound) 8.3 against 13.6 - more warps
+    // pay only there.
     static const int npt_env = [] { const char* e = getenv("PDX_ANISO_NPT"); return e ? atoi(e) : 0; }();
     if (math == PDX_MATH_EXACT)
         return npt_env == 4 ? launch_inst<MODEL, PDX_MATH_EXACT, 4>(a, m, s) : launch_inst<MODEL, PDX_MATH_EXACT, 2>(a, m, s);
