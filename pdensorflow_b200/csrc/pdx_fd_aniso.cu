@@ -11,7 +11,9 @@
 // Kernel: the K1 scheme (pdx_fd_tma.cu) with seven staged fields instead of one.  A CTA owns an 8 x 128 tile
 // of the (y,z) plane and marches along x; U and the six tensor components of a plane arrive as seven
 // cp.async.bulk.tensor boxes of 1 x 10 x 136 floats (halo included, zero filled outside the array) in one slot of a
-// 5-deep shared-memory ring (3 planes in use, 2 in flight; 188 KB + 36 KB of gates, one CTA per SM).  A thread evaluates N = 4 (8 warps
+// 5-deep shared-memory ring (188 KB + 36 KB of gates, one CTA per SM; slots are refilled two planes ahead - running the
+// ring three planes ahead, which the register rotation below would allow, measured slower: 89.5 vs 97.5 Gnode-steps/s).
+// The rows of the three planes in use live in registers and rotate with the march (see the loop).  A thread evaluates N = 4 (8 warps
 // per CTA; FAST) or 2 (16 warps; EXACT) consecutive z nodes from 64 / 128-bit shared-memory reads:
 //   flux(axis a, side s) = s 0.5 ( T_a + sum_{b != a} T_b ),
 //   T_a = (C_aa[s e_a] + C_aa[0]) (X[s e_a] - X[0]) / h_a,
