@@ -293,6 +293,7 @@ class PartitionedExplicitFEM:
         if self._hdl is not None and self.exchange == 'lists':
             self._install_push([[int(q) for q in h.buffer_ptrs] for h in self._hdl])
         self._cur = 0
+        self._graphs = {}
         self._primed = world == 1 or self._local
         self.nsteps_done = 0
 
@@ -432,7 +433,7 @@ class PartitionedExplicitFEM:
         nblk, rem = divmod(nsteps, block)
         if nblk:
             key = (block, self._cur, None if I0 is None else I0.data_ptr())
-            graphs = self.__dict__.setdefault('_graphs', {})
+            graphs = self._graphs
             if key not in graphs:
                 g = torch.cuda.CUDAGraph()
                 st = torch.cuda.Stream(device=self.device)

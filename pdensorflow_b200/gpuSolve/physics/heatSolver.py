@@ -3,6 +3,7 @@
 One implicit Euler step of the heat equation, (MASS + dt*STIFFNESS) U1 = MASS (U0 + dt*I0): the caller
 owns the time loop and passes t to step().  Per step: one SpMV launch + one PCG launch.
 """
+import os
 import numpy as np
 import torch
 
@@ -186,7 +187,6 @@ class HeatSolver:
                 id(getattr(self._Solver, '_A', None)), id(getattr(self._Solver, '_handle', None)), id(getattr(self._Solver, '_part', None)))
 
     def _graph_step(self, I0):
-        import os
         if os.environ.get('PDX_STEP_GRAPH', '1') == '0' or torch.cuda.is_current_stream_capturing():
             return self.solve_step(self._U, I0)
         key = (self._U.data_ptr(), I0.data_ptr(), self._step_token())

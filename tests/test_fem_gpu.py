@@ -120,6 +120,33 @@ def test_monodomain_solver_steps_match_oracle(cuda, rcm):
     assert model.solver().niters() % 5 == 0 and abs(model.solver().niters() - orc.niters[-1]) <= 5
 
 
+@pytest.mark.parametrize('explicit', [False, True])
+def test_graph_replayed_steps_are_bitwise_the_eager_ones(cuda, explicit, monkeypatch):
+    """MonodomainSolver.step replays a CUDA graph from the third visit of a (buffer, forcing, parameters, settings) key on
+    (HeatSolver._graph_step).  Same kernels with the same arguments: bitwise the eager loop, through two stimuli (new
+    forcing fields), a set_parameter and a set_maxiter in mid-run (both must invalidate the captured steps)."""
+    out = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('PDX_STEP_GRAPH', mode)
+        model, _ = _build_model(31, True, explicit=explicit)
+        ctime, its = 0.0, []
+        for i in range(70):
+            ctime += 0.1
+            if i == 45:
+                model.ionic_model().set_parameter('tau_d', 0.07)
+            if i == 55:
+                model.solver().set_maxiter(200)
+            model.step(ctime)
+            if not explicit and i % 10 == 9:
+                its.append(model.solver().niters())
+        ngraphs = sum(1 for v in model._step_graphs.values() if isinstance(v, tuple))
+        assert (ngraphs > 0) == (mode == '1')
+        out[mode] = (model.U().cpu().numpy(), model.ionic_state('_V_state').cpu().numpy(), its)
+    assert np.array_equal(out['1'][0], out['0'][0]) and np.array_equal(out['1'][1], out['0'][1])
+    assert out['1'][2] == out['0'][2]
+    assert out['1'][0].max() > -30.0
+
+
 def test_explicit_lumped_step_matches_oracle(cuda):
     """Row E (no reference implementation): explicit mass-lumped step vs its CPU restatement."""
     model, _ = _build_model(31, False, explicit=True, math='exact')
