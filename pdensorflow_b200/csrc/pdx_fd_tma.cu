@@ -447,7 +447,13 @@ int fd_tma_auto_chunk(const pdx_fd_desc& d) {
     }
     if (nplanes <= 1) return 1;
     const long long tiles = (long long)((d.ny + NWARP - 1) / NWARP) * ((d.nz + TZ - 1) / TZ);
+    // The two halo planes a chunk re-reads and its pipeline fill weigh more the less a plane costs: the heat equation
+    // (8 B per node, no ionic work) and the heterogeneous operator (two staged fields, 2 CTAs per SM) want longer marches
+    // (tools/chunk_variants.py on 512^3, profiles/r02_chunk_variants.jsonl: heat 671 -> 744 Gnode-steps/s at 24 planes,
+    // heterogeneous FK 163.8 -> 171.6; FK / mMS on the homogeneous operator are flat or lose beyond 8-12).
     int chunk = 8;
+    if (d.model == PDX_MODEL_NONE || (d.lap_kind == PDX_LAP_HETEROG && d.model == PDX_MODEL_FENTON4V)) chunk = 24;
+    else if (d.lap_kind == PDX_LAP_HETEROG) chunk = 16;
     while (chunk > 3 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * 3 * 2) --chunk;
     if (chunk > nplanes) chunk = nplanes;
     return chunk;
