@@ -389,7 +389,7 @@ int fd_aniso_auto_chunk(const pdx_fd_desc& d) {
     const int nplanes = d.x_end - d.x_begin;
     if (nplanes <= 1) return 1;
     const long long tiles = (long long)((d.ny + TY - 1) / TY) * ((d.nz + TZ - 1) / TZ);
-    int chunk = 32;
+    int chunk = 64;             // tools/chunk_variants2.py, 256 x 512^2 FK: 85.2 / 92.7 / 97.0 / 99.4 / 89.7 Gnode-steps/s at 8 / 16 / 32 / 64 / 128
     while (chunk > 4 && tiles * ((nplanes + chunk - 1) / chunk) < 2LL * sm_count()) chunk /= 2;
     return chunk < nplanes ? chunk : nplanes;
 }

@@ -441,7 +441,7 @@ int fd_tma_auto_chunk(const pdx_fd_desc& d) {
     const int nplanes = d.x_end - d.x_begin;
     if (d.ndim == 2) {          // y-tiles marched per CTA: as long as the grid still fills the SMs twice over
         const long long nty = (d.ny + NWARP - 1) / NWARP, ntz = (d.nz + TZ - 1) / TZ;
-        int chunk = 8;
+        int chunk = 4;          // tools/chunk_variants2.py: 4096^2 FK 188.1 Gnode-steps/s at 4 tiles, 184.0 at 8, 171.8 at 16
         while (chunk > 1 && ntz * ((nty + chunk - 1) / chunk) < 148LL * 3 * 2) --chunk;
         return chunk;
     }
